@@ -1,0 +1,85 @@
+"""ctypes binding of libasyrp_b200.so (the C-ABI in include/asyrp_b200.h).
+
+The library is the only compute path of this package: if it is missing or fails to load, importing the
+engine raises — there is no PyTorch / CPU fallback.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libasyrp_b200.so")
+
+c_void_p, c_int, c_float = C.c_void_p, C.c_int, C.c_float
+
+
+class AsyrpConvSeg(C.Structure):
+    _fields_ = [("src", c_void_p), ("C", c_int), ("mode", c_int)]
+
+
+class AsyrpConvDesc(C.Structure):
+    _fields_ = [
+        ("N", c_int), ("H", c_int), ("W", c_int), ("Cout", c_int),
+        ("nseg", c_int),
+        ("seg", AsyrpConvSeg * 3),
+        ("weight", c_void_p),
+        ("weight_batched", c_int),
+        ("ebias", c_void_p),
+        ("ebias_stride", c_int),
+        ("residual", c_void_p),
+        ("res_scale", c_float), ("acc_scale", c_float),
+        ("out", c_void_p),
+        ("stats", c_void_p),
+        ("out_planar", c_void_p),
+        ("planar_c", c_int),
+    ]
+
+
+# name -> (restype, argtypes); every symbol include/asyrp_b200.h declares
+SIGNATURES = {
+    "asyrp_last_error": (C.c_char_p, []),
+    "asyrp_conv_stats_tiles": (c_int, [c_int, c_int]),
+    "asyrp_conv_create": (c_int, [C.POINTER(AsyrpConvDesc), C.POINTER(c_void_p)]),
+    "asyrp_conv_launch": (c_int, [c_void_p, c_void_p]),
+    "asyrp_conv_destroy": (None, [c_void_p]),
+    "asyrp_gn_finalize": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_float,
+                                  c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
+    "asyrp_apply": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                            c_int, c_void_p]),
+    "asyrp_pack_input": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "asyrp_timestep_embedding": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "asyrp_linear": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                             c_int, c_void_p]),
+    "asyrp_ddim_update": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                  c_int, c_float, c_float, c_float, c_float, c_void_p]),
+    "asyrp_attention": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p]),
+}
+
+_lib = None
+
+
+class AsyrpError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (once) and attach prototypes.  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise AsyrpError(
+            f"{LIB_PATH} not found: build it with `python -m asyrp_official_b200.build` "
+            "(this package has no fallback path)")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = load().asyrp_last_error().decode(errors="replace")
+        raise AsyrpError(f"{what} failed (rc={rc}): {msg}")

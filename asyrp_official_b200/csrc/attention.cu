@@ -1,0 +1,153 @@
+// Self-attention over the spatial positions of one feature map (softmax(q k^T / sqrt(d)) v), fp16 in/out,
+// fp32 logits / softmax / accumulation.  Reference: AttnBlock.forward (ddpm/diffusion.py:200-225, one head,
+// d = C) and QKVAttentionLegacy.forward (improved_ddpm/unet.py:379-396, heads of 64 channels, q and k each
+// scaled by d^-1/4, softmax in fp32).  The q/k/v projections and proj_out run on the tcgen05 GEMM kernel
+// (conv_gemm.cu); this kernel is the T x T part with a warp-level online softmax.
+//
+// Layout: qkv [N][T][3*C] with C = heads*D: q at [0,C), k at [C,2C), v at [2C,3C), head h at h*D.
+// Block = 8 warps; each warp owns 2 queries; keys/values streamed through shared memory 32 at a time.
+#include "common.h"
+#include "ptx.cuh"
+
+namespace asyrp {
+
+template <int D>
+__global__ void __launch_bounds__(256) attention_kernel(const __half* __restrict__ qkv, __half* __restrict__ out,
+                                                        int T, int heads, float scale) {
+  constexpr int QT = 16, KT = 32, KS = D + 8;  // padded key row stride (halves): conflict-free 16B reads
+  extern __shared__ __align__(16) uint8_t smem_attn[];
+  __half* sq = reinterpret_cast<__half*>(smem_attn);  // [QT][D]
+  __half* sk = sq + QT * D;                           // [KT][KS]
+  __half* sv = sk + KT * KS;                          // [KT][D]
+
+  const int n = blockIdx.z, head = blockIdx.y, q0 = blockIdx.x * QT;
+  const int C = heads * D;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const __half* base = qkv + static_cast<size_t>(n) * T * 3 * C;
+
+  // stage the query tile
+  for (int i = threadIdx.x; i < QT * (D / 8); i += blockDim.x) {
+    const int r = i / (D / 8), c8 = i % (D / 8);
+    uint4 u = make_uint4(0, 0, 0, 0);
+    if (q0 + r < T) u = *reinterpret_cast<const uint4*>(base + static_cast<size_t>(q0 + r) * 3 * C + head * D + c8 * 8);
+    *reinterpret_cast<uint4*>(sq + r * D + c8 * 8) = u;
+  }
+
+  float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+  float2 acc[2][D / 64];
+#pragma unroll
+  for (int qi = 0; qi < 2; ++qi)
+#pragma unroll
+    for (int j = 0; j < D / 64; ++j) acc[qi][j] = make_float2(0.f, 0.f);
+
+  for (int k0 = 0; k0 < T; k0 += KT) {
+    __syncthreads();  // previous tile fully consumed (also covers the sq staging on the first pass)
+    for (int i = threadIdx.x; i < KT * (D / 8); i += blockDim.x) {
+      const int r = i / (D / 8), c8 = i % (D / 8);
+      uint4 uk = make_uint4(0, 0, 0, 0), uv = make_uint4(0, 0, 0, 0);
+      if (k0 + r < T) {
+        const __half* row = base + static_cast<size_t>(k0 + r) * 3 * C + head * D + c8 * 8;
+        uk = *reinterpret_cast<const uint4*>(row + C);
+        uv = *reinterpret_cast<const uint4*>(row + 2 * C);
+      }
+      *reinterpret_cast<uint4*>(sk + r * KS + c8 * 8) = uk;
+      *reinterpret_cast<uint4*>(sv + r * D + c8 * 8) = uv;
+    }
+    __syncthreads();
+
+#pragma unroll
+    for (int qi = 0; qi < 2; ++qi) {
+      const __half* qrow = sq + (warp * 2 + qi) * D;
+      const __half* krow = sk + lane * KS;
+      float s = 0.f;
+#pragma unroll 4
+      for (int c8 = 0; c8 < D / 8; ++c8) {
+        const uint4 uq = *reinterpret_cast<const uint4*>(qrow + c8 * 8);
+        const uint4 uk = *reinterpret_cast<const uint4*>(krow + c8 * 8);
+        const __half2* hq = reinterpret_cast<const __half2*>(&uq);
+        const __half2* hk = reinterpret_cast<const __half2*>(&uk);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 a = __half22float2(hq[k]), b = __half22float2(hk[k]);
+          s = fmaf(a.x, b.x, s);
+          s = fmaf(a.y, b.y, s);
+        }
+      }
+      s = (k0 + lane < T) ? s * scale : -INFINITY;
+      float mx = s;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      const float m_new = fmaxf(m_run[qi], mx);
+      const float corr = __expf(m_run[qi] - m_new);
+      const float pr = __expf(s - m_new);
+      float ps = pr;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) ps += __shfl_xor_sync(0xffffffffu, ps, o);
+      l_run[qi] = l_run[qi] * corr + ps;
+      m_run[qi] = m_new;
+#pragma unroll
+      for (int j = 0; j < D / 64; ++j) {
+        acc[qi][j].x *= corr;
+        acc[qi][j].y *= corr;
+      }
+#pragma unroll 8
+      for (int kk = 0; kk < KT; ++kk) {
+        const float pk = __shfl_sync(0xffffffffu, pr, kk);
+        const __half* vrow = sv + kk * D + 2 * lane;
+#pragma unroll
+        for (int j = 0; j < D / 64; ++j) {
+          const float2 vv = __half22float2(*reinterpret_cast<const __half2*>(vrow + 64 * j));
+          acc[qi][j].x = fmaf(pk, vv.x, acc[qi][j].x);
+          acc[qi][j].y = fmaf(pk, vv.y, acc[qi][j].y);
+        }
+      }
+    }
+  }
+
+#pragma unroll
+  for (int qi = 0; qi < 2; ++qi) {
+    const int t = q0 + warp * 2 + qi;
+    if (t < T) {
+      const float inv = 1.0f / l_run[qi];
+      __half* orow = out + (static_cast<size_t>(n) * T + t) * C + head * D + 2 * lane;
+#pragma unroll
+      for (int j = 0; j < D / 64; ++j)
+        *reinterpret_cast<__half2*>(orow + 64 * j) = __floats2half2_rn(acc[qi][j].x * inv, acc[qi][j].y * inv);
+    }
+  }
+}
+
+template <int D>
+static int launch_attention(const void* qkv, void* out, int N, int T, int heads, float scale, cudaStream_t st) {
+  constexpr int QT = 16, KT = 32, KS = D + 8;
+  const size_t smem = (QT * D + KT * KS + KT * D) * sizeof(__half);
+  static bool attr_set = false;
+  if (!attr_set) {
+    ASYRP_CHECK_CUDA(
+        cudaFuncSetAttribute(attention_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    attr_set = true;
+  }
+  dim3 grid((T + QT - 1) / QT, heads, N);
+  attention_kernel<D><<<grid, 256, smem, st>>>(static_cast<const __half*>(qkv), static_cast<__half*>(out), T, heads,
+                                              scale);
+  ASYRP_CHECK_CUDA(cudaGetLastError());
+  return ASYRP_OK;
+}
+
+}  // namespace asyrp
+
+using namespace asyrp;
+
+extern "C" ASYRP_API int asyrp_attention(const void* qkv, void* out, int N, int T, int heads, int head_dim,
+                                         float scale, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (head_dim) {
+    case 64: return launch_attention<64>(qkv, out, N, T, heads, scale, st);
+    case 128: return launch_attention<128>(qkv, out, N, T, heads, scale, st);
+    case 256: return launch_attention<256>(qkv, out, N, T, heads, scale, st);
+    case 512: return launch_attention<512>(qkv, out, N, T, heads, scale, st);
+    default:
+      set_error("asyrp_attention: unsupported head_dim %d (supported 64/128/256/512)", head_dim);
+      return ASYRP_ERR_INVALID;
+  }
+}

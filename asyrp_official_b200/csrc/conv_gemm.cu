@@ -1,0 +1,529 @@
+// Implicit-GEMM convolution / batched GEMM on tcgen05 tensor cores (sm_100a), TMA-fed.
+//
+// One kernel serves every dense contraction of the Asyrp UNet path:
+//   * 3x3 stride-1 pad-1 convs        (ResnetBlock.conv1/conv2, Upsample.conv; ddpm/diffusion.py:122-133,77-81)
+//   * 3x3 stride-2 convs, pad (0,1,0,1) (Downsample.conv; ddpm/diffusion.py:96-107)
+//   * 1x1 convs                        (nin_shortcut :145-149, AttnBlock q/k/v/proj :179-198, DeltaBlock :236-249,
+//                                       improved_ddpm/unet.py qkv/proj_out :333-336, skip_connection :264)
+//   * plain GEMMs (rows = "pixels" of an H=1 image)
+//
+// Data layout: activations NHWC fp16, weights [Cout][K] fp16 with K = sum over segments of taps*C_seg
+// (tap-major, channel-minor), accumulation fp32 in TMEM, epilogue fp32.
+//
+// The K loop walks "segments": each segment is one source tensor (so a channel-concat input is two
+// segments and never materialised; a fused 1x1 shortcut is one more segment accumulated into the same
+// TMEM tile).  For a 3x3/s1 segment the producer loads, per 64-channel chunk, three dx-shifted copies of
+// the (TH+2)-row halo tile; the three dy taps of a copy are 1024B-aligned row offsets into it, so every
+// tap is a canonical K-major SWIZZLE_128B operand and TMA's out-of-bounds zero fill is the padding.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
+// warps 2..5 = epilogue (TMEM -> registers -> bias/residual -> fp16 NHWC store + GroupNorm partial sums).
+// Persistent: each CTA loops over output tiles (128 pixels x BN channels); two TMEM accumulators so the
+// epilogue of tile i overlaps the MMAs of tile i+1.
+#include "common.h"
+#include "ptx.cuh"
+#include <cstring>
+
+namespace asyrp {
+
+static constexpr int kMaxSeg = 3;
+static constexpr int kNumThreads = 192;
+
+struct ConvSegDev {
+  int nchunks;  // C / 64
+  int mode;     // 0: 1x1, 1: 3x3 stride 1, 2: 3x3 stride 2 (parity view)
+  int kbase;    // first K column of this segment in the weight matrix
+  int C;        // channels of the source
+};
+
+struct ConvParams {
+  CUtensorMap tmA[kMaxSeg];
+  CUtensorMap tmB;
+  ConvSegDev seg[kMaxSeg];
+  int nseg;
+  int N, H, W, Cout;      // output geometry
+  int TW, TH, NB;         // pixel tile: TW x TH pixels of NB samples, TW*TH*NB == 128
+  int tiles_x, tiles_y, tiles_n, m_tiles, n_tiles;
+  int a_stages, b_stages;
+  uint32_t a_stage_bytes;  // ring slot size for A copies
+  uint32_t row_bytes;      // NB*TW*128 : bytes of one tile row (all samples) of one 64-channel chunk
+  const float* ebias;      // fp32 bias (+ timestep-embedding projection): row n at ebias + n*ebias_stride
+  int ebias_stride;        // 0: one row shared by all samples
+  const __half* res;       // residual, NHWC like out, or nullptr
+  float res_scale, acc_scale;
+  __half* out;             // [N][H][W][Cout] fp16, or nullptr when out_planar is used
+  float* out_planar;       // optional fp32 planar [N][planar_c][H][W] holding output channels [0, planar_c)
+  int planar_c;
+  float* stats;            // [N][tiles_y*tiles_x][Cout/2][2] partial (sum, sumsq) or nullptr
+  int b_batched;           // weights have a per-sample batch dimension (attention GEMMs)
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B operands need 1024B alignment
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  constexpr uint32_t kBStage = BN * 128;
+  constexpr uint32_t kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
+
+  uint8_t* sA = smem;
+  uint8_t* sB = sA + p.a_stages * p.a_stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + p.b_stages * kBStage);
+  uint64_t* fullA = bars;
+  uint64_t* emptyA = fullA + p.a_stages;
+  uint64_t* fullB = emptyA + p.a_stages;
+  uint64_t* emptyB = fullB + p.b_stages;
+  uint64_t* tfull = emptyB + p.b_stages;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* s_stats = reinterpret_cast<float*>(tmem_slot + 4);  // [2][4][BN/32][32]
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.a_stages; ++i) {
+      mbar_init(&fullA[i], 1);
+      mbar_init(&emptyA[i], 1);
+    }
+    for (int i = 0; i < p.b_stages; ++i) {
+      mbar_init(&fullB[i], 1);
+      mbar_init(&emptyB[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.nseg; ++s) tma_prefetch_desc(&p.tmA[s]);
+    tma_prefetch_desc(&p.tmB);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_tiles = p.m_tiles * p.n_tiles;
+
+  if (warp == 0) {
+    // ======================================================== TMA producer
+    if (lane == 0) {
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int mt = tile % p.m_tiles, nt = tile / p.m_tiles;
+        const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, tn = mt / (p.tiles_x * p.tiles_y);
+        const int x0 = tx * p.TW, y0 = ty * p.TH, n0 = tn * p.NB;
+        const int bz = p.b_batched ? n0 : 0;
+        for (int s = 0; s < p.nseg; ++s) {
+          const ConvSegDev sg = p.seg[s];
+          const int ncopies = sg.mode == 0 ? 1 : (sg.mode == 1 ? 3 : 9);
+          const int ntaps = sg.mode == 1 ? 3 : 1;
+          const uint32_t a_bytes = (sg.mode == 1 ? (p.TH + 2) : p.TH) * p.row_bytes;
+          for (int ch = 0; ch < sg.nchunks; ++ch) {
+            for (int cp = 0; cp < ncopies; ++cp) {
+              mbar_wait(&emptyA[sa], pa ^ 1);
+              mbar_arrive_expect_tx(&fullA[sa], a_bytes);
+              uint8_t* dst = sA + sa * p.a_stage_bytes;
+              if (sg.mode == 0) {
+                tma_load_5d(dst, &p.tmA[s], &fullA[sa], ch * 64, x0, n0, 0, y0);
+              } else if (sg.mode == 1) {
+                tma_load_5d(dst, &p.tmA[s], &fullA[sa], ch * 64, x0 + cp - 1, n0, 0, y0 - 1);
+              } else {
+                const int ky = cp / 3, kx = cp % 3;
+                tma_load_5d(dst, &p.tmA[s], &fullA[sa], ch * 64 + (kx & 1) * sg.C, x0 + (kx >> 1), n0, ky & 1,
+                            y0 + (ky >> 1));
+              }
+              if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
+              for (int tp = 0; tp < ntaps; ++tp) {
+                // tap index in the weight matrix: ky*3+kx
+                const int tap = sg.mode == 0 ? 0 : (sg.mode == 1 ? tp * 3 + cp : cp);
+                mbar_wait(&emptyB[sb], pb ^ 1);
+                mbar_arrive_expect_tx(&fullB[sb], kBStage);
+                tma_load_3d(sB + sb * kBStage, &p.tmB, &fullB[sb], sg.kbase + tap * sg.C + ch * 64, nt * BN, bz);
+                if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ======================================================== MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16_m128(BN);
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        uint32_t accumulate = 0;
+        for (int s = 0; s < p.nseg; ++s) {
+          const ConvSegDev sg = p.seg[s];
+          const int ncopies = sg.mode == 0 ? 1 : (sg.mode == 1 ? 3 : 9);
+          const int ntaps = sg.mode == 1 ? 3 : 1;
+          for (int ch = 0; ch < sg.nchunks; ++ch) {
+            for (int cp = 0; cp < ncopies; ++cp) {
+              mbar_wait(&fullA[sa], pa);
+              tc_fence_after();
+              const uint32_t a_base = smem_u32(sA + sa * p.a_stage_bytes);
+              for (int tp = 0; tp < ntaps; ++tp) {
+                mbar_wait(&fullB[sb], pb);
+                tc_fence_after();
+                const uint32_t a_addr = a_base + tp * p.row_bytes;  // dy tap = row shift (mode 1)
+                const uint32_t b_addr = smem_u32(sB + sb * kBStage);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  umma_f16(d_tmem, umma_desc_k128(a_addr + k * 32), umma_desc_k128(b_addr + k * 32), idesc,
+                           accumulate);
+                  accumulate = 1;
+                }
+                umma_commit(&emptyB[sb]);
+                if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
+              }
+              umma_commit(&emptyA[sa]);
+              if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
+            }
+          }
+        }
+        umma_commit(&tfull[acc]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ======================================================== epilogue (warps 2..5)
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int ep_tid = (warp - 2) * 32 + lane;
+    const int row = q * 32 + lane;
+    const int xx = row % p.TW, nn = (row / p.TW) % p.NB, yy = row / (p.TW * p.NB);
+    const int tiles_per_sample = p.tiles_x * p.tiles_y;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int mt = tile % p.m_tiles, nt = tile / p.m_tiles;
+      const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, tn = mt / tiles_per_sample;
+      const int x = tx * p.TW + xx, y = ty * p.TH + yy, n = tn * p.NB + nn;
+      const bool valid = (x < p.W) && (y < p.H) && (n < p.N);
+      const size_t pix = (static_cast<size_t>(n) * p.H + y) * p.W + x;
+      float* st = s_stats + acc * (4 * BN);
+
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int cc = 0; cc < BN / 32; ++cc) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + cc * 32, r);
+        tmem_ld_wait();
+        const int c0 = nt * BN + cc * 32;
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+        if (p.ebias != nullptr) {
+          const float* eb = p.ebias + static_cast<size_t>(valid ? n : 0) * p.ebias_stride + c0;
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(eb + i);
+            v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+          }
+        }
+        if (p.acc_scale != 1.0f) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] *= p.acc_scale;
+        }
+        if (p.res != nullptr && valid) {
+          const uint4* rp = reinterpret_cast<const uint4*>(p.res + pix * p.Cout + c0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 u = rp[j];
+            const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float2 f = __half22float2(h2[k]);
+              v[j * 8 + k * 2] += p.res_scale * f.x;
+              v[j * 8 + k * 2 + 1] += p.res_scale * f.y;
+            }
+          }
+        }
+        if (p.out_planar != nullptr) {
+          if (valid && c0 == 0) {
+            const size_t hw = static_cast<size_t>(p.H) * p.W;
+            float* pp = p.out_planar + static_cast<size_t>(n) * p.planar_c * hw + static_cast<size_t>(y) * p.W + x;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              if (i < p.planar_c) pp[i * hw] = v[i];
+          }
+        } else if (valid) {
+          uint4* op = reinterpret_cast<uint4*>(p.out + pix * p.Cout + c0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 u;
+            __half2* h2 = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) h2[k] = __floats2half2_rn(v[j * 8 + k * 2], v[j * 8 + k * 2 + 1]);
+            op[j] = u;
+          }
+        }
+        if (p.stats != nullptr) {
+          // per-sample partial sums over this warp's 32 pixels, at channel-pair granularity:
+          // slot j<16 : sum of pair j ; slot j>=16 : sum of squares of pair j-16
+          for (int sn = 0; sn < p.NB; ++sn) {
+            const bool mine = valid && (nn == sn);
+            float w[32];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float a = mine ? v[2 * j] : 0.f, b = mine ? v[2 * j + 1] : 0.f;
+              w[j] = a + b;
+              w[16 + j] = a * a + b * b;
+            }
+            // recursive-halving reduce-scatter: after the loop w[0] on lane L is the warp total of slot L
+#pragma unroll
+            for (int h = 16; h >= 1; h >>= 1) {
+              const bool up = (lane & h) != 0;
+#pragma unroll
+              for (int i = 0; i < h; ++i) {
+                const float send = up ? w[i] : w[i + h];
+                const float keep = up ? w[i + h] : w[i];
+                w[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+              }
+            }
+            // s_stats[acc][sn?]: NB>1 tiles are tiny layers; fold sn into the slot by direct global write
+            if (p.NB == 1) {
+              st[(q * (BN / 32) + cc) * 32 + lane] = w[0];
+            } else {
+              // one atomic per (warp, sample, slot): few tiles, low contention, fp32 order-dependent only
+              // across the 4 warps of a tile -> made deterministic by writing per-warp slots
+              const int ns = tn * p.NB + sn;
+              if (ns < p.N) {
+                const int tile_in_sample = ty * p.tiles_x + tx;
+                float* g = p.stats + (((static_cast<size_t>(ns) * tiles_per_sample + tile_in_sample) * 4 + q) *
+                                          (p.Cout / 2) + (c0 / 2) + (lane & 15)) * 2 + (lane >> 4);
+                *g = w[0];
+              }
+            }
+          }
+        }
+      }
+      // accumulator fully drained into registers/global: release it to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+
+      if (p.stats != nullptr && p.NB == 1) {
+        named_bar_sync(1, 128);
+        // 128 threads: one (chunk, slot) each for BN=128; loop for other BN
+        for (int e = ep_tid; e < BN; e += 128) {
+          const int cc = e >> 5, j = e & 31;
+          float tot = 0.f;
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq) tot += st[(qq * (BN / 32) + cc) * 32 + j];
+          const int tile_in_sample = ty * p.tiles_x + tx;
+          float* g = p.stats + ((static_cast<size_t>(tn) * tiles_per_sample + tile_in_sample) * (p.Cout / 2) +
+                                (nt * BN + cc * 32) / 2 + (j & 15)) * 2 + (j >> 4);
+          *g = tot;
+        }
+      }
+    }
+  }
+
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host side
+// ------------------------------------------------------------------------------------------------
+struct ConvOp {
+  ConvParams p;
+  int BN;
+  int grid;
+  size_t smem_bytes;
+};
+
+}  // namespace asyrp
+
+using namespace asyrp;
+
+extern "C" {
+
+struct AsyrpConvSeg {
+  const void* src;  // fp16 NHWC source tensor
+  int C;            // its channel count (multiple of 64)
+  int mode;         // 0: 1x1, 1: 3x3 s1 p1, 2: 3x3 s2 pad(0,1,0,1) (source is [N][2H][2W][C])
+};
+
+struct AsyrpConvDesc {
+  int N, H, W, Cout;  // output geometry (NHWC)
+  int nseg;
+  AsyrpConvSeg seg[3];
+  const void* weight;  // fp16 [batch?][Cout][Ktot]
+  int weight_batched;  // 1: one weight matrix per sample (requires 128-row tiles within one sample)
+  const float* ebias;  // fp32, row n at ebias + n*ebias_stride (stride 0: shared row), or null
+  int ebias_stride;
+  const void* residual;  // fp16 NHWC [N][H][W][Cout] or null
+  float res_scale, acc_scale;
+  void* out;     // fp16 NHWC (ignored when out_planar is set)
+  float* stats;  // partial GroupNorm sums, see asyrp_conv_stats_tiles()
+  float* out_planar;  // optional: fp32 NCHW [N][planar_c][H][W] receiving output channels [0, planar_c<=8)
+  int planar_c;
+};
+
+static void conv_tile_shape(int H, int W, int* TW, int* TH, int* NB) {
+  int tw, th;
+  if (H == 1) {
+    tw = W < 128 ? W : 128;
+    th = 1;
+  } else {
+    tw = W < 16 ? W : 16;
+    th = 128 / tw;
+    if (th > 8) th = 8;
+    if (th > H) th = H;
+  }
+  // largest power-of-two tile that divides 128
+  while (128 % (tw * th) != 0) --th;
+  *TW = tw;
+  *TH = th;
+  *NB = 128 / (tw * th);
+}
+
+// number of pixel tiles per sample the stats buffer must hold: stats is [N][tiles][Cout/2][2] floats.
+// For layers whose tile spans several samples (NB>1) the kernel writes one slot per epilogue warp (4).
+ASYRP_API int asyrp_conv_stats_tiles(int H, int W) {
+  int TW, TH, NB;
+  conv_tile_shape(H, W, &TW, &TH, &NB);
+  const int tiles = ((W + TW - 1) / TW) * ((H + TH - 1) / TH);
+  return NB == 1 ? tiles : tiles * 4;
+}
+
+ASYRP_API int asyrp_conv_create(const AsyrpConvDesc* d, void** out_op) {
+  ASYRP_REQUIRE(d && out_op, "asyrp_conv_create: null argument");
+  ASYRP_REQUIRE(d->nseg >= 1 && d->nseg <= kMaxSeg, "asyrp_conv_create: nseg=%d out of range", d->nseg);
+  ASYRP_REQUIRE(d->Cout % 64 == 0, "asyrp_conv_create: Cout=%d must be a multiple of 64", d->Cout);
+  ConvOp* op = new ConvOp();
+  ConvParams& p = op->p;
+  memset(&p, 0, sizeof(p));
+  p.N = d->N; p.H = d->H; p.W = d->W; p.Cout = d->Cout;
+  conv_tile_shape(d->H, d->W, &p.TW, &p.TH, &p.NB);
+  ASYRP_REQUIRE(p.TW * p.TH * p.NB == 128, "asyrp_conv_create: cannot tile H=%d W=%d into 128 pixels", d->H,
+                d->W);
+  ASYRP_REQUIRE(!(d->weight_batched && p.NB != 1), "asyrp_conv_create: batched weights need NB==1");
+  p.tiles_x = (d->W + p.TW - 1) / p.TW;
+  p.tiles_y = (d->H + p.TH - 1) / p.TH;
+  p.tiles_n = (d->N + p.NB - 1) / p.NB;
+  p.m_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
+  op->BN = (d->Cout % 256 == 0) ? 256 : (d->Cout % 128 == 0 ? 128 : 64);
+  p.n_tiles = d->Cout / op->BN;
+  p.row_bytes = p.NB * p.TW * 128;
+  p.nseg = d->nseg;
+  bool any3 = false;
+  int ktot = 0;
+  for (int s = 0; s < d->nseg; ++s) {
+    const AsyrpConvSeg& sg = d->seg[s];
+    ASYRP_REQUIRE(sg.C % 64 == 0 && sg.C > 0, "asyrp_conv_create: segment channels %d not a multiple of 64", sg.C);
+    ASYRP_REQUIRE(sg.mode >= 0 && sg.mode <= 2, "asyrp_conv_create: bad segment mode %d", sg.mode);
+    p.seg[s].nchunks = sg.C / 64;
+    p.seg[s].mode = sg.mode;
+    p.seg[s].kbase = ktot;
+    p.seg[s].C = sg.C;
+    ktot += (sg.mode == 0 ? 1 : 9) * sg.C;
+    any3 = any3 || sg.mode == 1;
+    uint64_t dims[5], strides[4];
+    uint32_t box[5];
+    const uint64_t C = sg.C;
+    if (sg.mode != 2) {
+      const uint64_t H = d->H, W = d->W;
+      dims[0] = C; dims[1] = W; dims[2] = d->N; dims[3] = 1; dims[4] = H;
+      strides[0] = C * 2; strides[1] = H * W * C * 2; strides[2] = W * C * 2; strides[3] = W * C * 2;
+      box[0] = 64; box[1] = p.TW; box[2] = p.NB; box[3] = 1; box[4] = sg.mode == 1 ? p.TH + 2 : p.TH;
+    } else {
+      const uint64_t Hi = 2 * d->H, Wi = 2 * d->W;
+      dims[0] = 2 * C; dims[1] = Wi / 2; dims[2] = d->N; dims[3] = 2; dims[4] = Hi / 2;
+      strides[0] = 2 * C * 2; strides[1] = Hi * Wi * C * 2; strides[2] = Wi * C * 2; strides[3] = 2 * Wi * C * 2;
+      box[0] = 64; box[1] = p.TW; box[2] = p.NB; box[3] = 1; box[4] = p.TH;
+    }
+    int rc = encode_tensor_map(&p.tmA[s], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, sg.src, dims, strides, box,
+                               CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc != ASYRP_OK) { delete op; return rc; }
+  }
+  {
+    uint64_t dims[3] = {static_cast<uint64_t>(ktot), static_cast<uint64_t>(d->Cout),
+                        static_cast<uint64_t>(d->weight_batched ? d->N : 1)};
+    uint64_t strides[2] = {static_cast<uint64_t>(ktot) * 2, static_cast<uint64_t>(ktot) * d->Cout * 2};
+    uint32_t box[3] = {64, static_cast<uint32_t>(op->BN), 1};
+    int rc = encode_tensor_map(&p.tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, d->weight, dims, strides, box,
+                               CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc != ASYRP_OK) { delete op; return rc; }
+  }
+  p.b_batched = d->weight_batched;
+  p.a_stage_bytes = (any3 ? p.TH + 2 : p.TH) * p.row_bytes;
+  // shared memory budget: ~205 KB of operand rings
+  const uint32_t b_stage = op->BN * 128;
+  p.a_stages = any3 ? 4 : 4;
+  p.b_stages = op->BN == 256 ? 4 : 6;
+  while (p.a_stages * p.a_stage_bytes + p.b_stages * b_stage > 210 * 1024 && p.a_stages > 2) --p.a_stages;
+  while (p.a_stages * p.a_stage_bytes + p.b_stages * b_stage > 210 * 1024 && p.b_stages > 2) --p.b_stages;
+  p.ebias = d->ebias;
+  p.ebias_stride = d->ebias_stride;
+  p.out_planar = d->out_planar;
+  p.planar_c = d->planar_c;
+  ASYRP_REQUIRE(d->out_planar == nullptr || (d->planar_c >= 1 && d->planar_c <= 8),
+                "asyrp_conv_create: planar_c=%d out of range", d->planar_c);
+  p.res = static_cast<const __half*>(d->residual);
+  p.res_scale = d->res_scale;
+  p.acc_scale = d->acc_scale;
+  p.out = static_cast<__half*>(d->out);
+  p.stats = d->stats;
+  op->smem_bytes = 1024 + static_cast<size_t>(p.a_stages) * p.a_stage_bytes +
+                   static_cast<size_t>(p.b_stages) * b_stage + (2 * (p.a_stages + p.b_stages) + 4) * 8 + 16 +
+                   2 * 4 * op->BN * 4;
+  ASYRP_REQUIRE(op->smem_bytes <= 227 * 1024, "asyrp_conv_create: smem %zu too large", op->smem_bytes);
+  const int sms = sm_count();
+  if (sms <= 0) { delete op; return ASYRP_ERR_NO_DEVICE; }
+  const int total = p.m_tiles * p.n_tiles;
+  op->grid = total < sms ? total : sms;
+  cudaError_t e = cudaSuccess;
+  if (op->BN == 256)
+    e = cudaFuncSetAttribute(conv_gemm_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  else if (op->BN == 128)
+    e = cudaFuncSetAttribute(conv_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  else
+    e = cudaFuncSetAttribute(conv_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) {
+    set_error("asyrp_conv_create: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    delete op;
+    return ASYRP_ERR_CUDA;
+  }
+  *out_op = op;
+  return ASYRP_OK;
+}
+
+ASYRP_API int asyrp_conv_launch(void* handle, void* stream) {
+  ASYRP_REQUIRE(handle, "asyrp_conv_launch: null op");
+  ConvOp* op = static_cast<ConvOp*>(handle);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (op->BN == 256)
+    conv_gemm_kernel<256><<<op->grid, kNumThreads, op->smem_bytes, st>>>(op->p);
+  else if (op->BN == 128)
+    conv_gemm_kernel<128><<<op->grid, kNumThreads, op->smem_bytes, st>>>(op->p);
+  else
+    conv_gemm_kernel<64><<<op->grid, kNumThreads, op->smem_bytes, st>>>(op->p);
+  ASYRP_CHECK_CUDA(cudaGetLastError());
+  return ASYRP_OK;
+}
+
+ASYRP_API void asyrp_conv_destroy(void* handle) { delete static_cast<ConvOp*>(handle); }
+
+}  // extern "C"

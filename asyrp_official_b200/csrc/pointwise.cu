@@ -1,0 +1,347 @@
+// HBM-bound kernels of the Asyrp path: GroupNorm finalise / apply (+SiLU, +2x resample, +concat), input
+// packing, timestep embedding + small linears, and the DDIM update.  All activations NHWC fp16; statistics,
+// affine tables, embeddings and the sampler state x_t are fp32.
+#include "common.h"
+#include "ptx.cuh"
+
+namespace asyrp {
+
+// ---------------------------------------------------------------------------------------------
+// GroupNorm finalise: partial (sum, sumsq) per (sample, tile, channel pair) -> per-(sample, channel)
+// affine (a, b) with y = a*x + b  ==  GroupNorm(32 groups, eps) [* (1+scale) + shift].
+// Reference: torch.nn.GroupNorm in Normalize (ddpm/diffusion.py:68-69, eps 1e-6) and GroupNorm32
+// (improved_ddpm/nn.py:17-19, eps 1e-5); scale/shift: improved_ddpm/unet.py:290-294.
+// The input may be the channel concatenation of two tensors (decoder skip concat, ddpm/diffusion.py:549,567):
+// groups are formed over the virtual concatenated channel axis and may straddle the seam.
+// ---------------------------------------------------------------------------------------------
+__global__ void gn_finalize_kernel(const float* __restrict__ st_a, int Ca, int Ta, const float* __restrict__ st_b,
+                                   int Cb, int Tb, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float eps, float count, const float* __restrict__ scale_shift, int ss_stride,
+                                   float* __restrict__ affine) {
+  const int g = blockIdx.x, n = blockIdx.y;
+  const int C = Ca + Cb, cpg = C / 32;
+  const int c_lo = g * cpg;
+  double s = 0.0, ss = 0.0;
+  // pairs of this group in source a and b
+  const int pairs = cpg / 2;
+  for (int pi = 0; pi < pairs; ++pi) {
+    const int c = c_lo + pi * 2;
+    const float* base;
+    int T, Cs, cc;
+    if (c < Ca) { base = st_a; T = Ta; Cs = Ca; cc = c; }
+    else { base = st_b; T = Tb; Cs = Cb; cc = c - Ca; }
+    const float* pbase = base + (static_cast<size_t>(n) * T * (Cs / 2) + cc / 2) * 2;
+    for (int t = threadIdx.x; t < T; t += blockDim.x) {
+      const float2 v = *reinterpret_cast<const float2*>(pbase + static_cast<size_t>(t) * (Cs / 2) * 2);
+      s += v.x;
+      ss += v.y;
+    }
+  }
+  __shared__ double sh_s[32], sh_ss[32];
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  }
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { sh_s[w] = s; sh_ss[w] = ss; }
+  __syncthreads();
+  if (w == 0) {
+    const int nw = blockDim.x >> 5;
+    s = l < nw ? sh_s[l] : 0.0;
+    ss = l < nw ? sh_ss[l] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    }
+    const double mean = s / count;
+    double var = ss / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    const float fmean = static_cast<float>(mean);
+    for (int i = l; i < cpg; i += 32) {
+      const int c = c_lo + i;
+      float a = gamma[c] * rstd;
+      float b = beta[c] - fmean * a;
+      if (scale_shift != nullptr) {
+        const float sc = 1.0f + scale_shift[static_cast<size_t>(n) * ss_stride + c];
+        const float sh = scale_shift[static_cast<size_t>(n) * ss_stride + C + c];
+        a = a * sc;
+        b = b * sc + sh;
+      }
+      affine[(static_cast<size_t>(n) * C + c) * 2] = a;
+      affine[(static_cast<size_t>(n) * C + c) * 2 + 1] = b;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Pointwise apply: out = resample(act(a*x + b)) over the channel concat of up to two sources.
+//   act: 0 identity, 1 SiLU (nonlinearity ddpm/diffusion.py:63-65 / nn.SiLU)
+//   resample: 0 none, 1 2x2 average pool (improved_ddpm/unet.py Downsample use_conv=False :173-181),
+//             2 nearest x2 (F.interpolate, ddpm/diffusion.py:83-84, improved_ddpm/unet.py:142-150)
+// One thread = 8 channels (16 B) of one output pixel.
+// ---------------------------------------------------------------------------------------------
+struct ApplyParams {
+  const __half* src_a; int Ca;
+  const __half* src_b; int Cb;
+  const float* affine;  // [N][C][2] or nullptr (identity)
+  __half* out;
+  int N, Hi, Wi, Ho, Wo;
+  int act, resample;
+};
+
+__device__ __forceinline__ void load8(const __half* p, float (&f)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float2 t = __half22float2(h[k]);
+    f[2 * k] = t.x;
+    f[2 * k + 1] = t.y;
+  }
+}
+__device__ __forceinline__ void store8(__half* p, const float (&f)[8]) {
+  uint4 u;
+  __half2* h = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) h[k] = __floats2half2_rn(f[2 * k], f[2 * k + 1]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+
+__global__ void __launch_bounds__(256) apply_kernel(const ApplyParams p) {
+  const int C = p.Ca + p.Cb;
+  const int oct_per_pix = C / 8;
+  const size_t total = static_cast<size_t>(p.N) * p.Ho * p.Wo * oct_per_pix;
+  for (size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int oc = static_cast<int>(idx % oct_per_pix);
+    size_t pix = idx / oct_per_pix;
+    const int xo = static_cast<int>(pix % p.Wo);
+    pix /= p.Wo;
+    const int yo = static_cast<int>(pix % p.Ho);
+    const int n = static_cast<int>(pix / p.Ho);
+    const int c = oc * 8;
+    const __half* src;
+    int Cs, cs;
+    if (c < p.Ca) { src = p.src_a; Cs = p.Ca; cs = c; }
+    else { src = p.src_b; Cs = p.Cb; cs = c - p.Ca; }
+    float a[8], b[8];
+    if (p.affine != nullptr) {
+      const float4* ap = reinterpret_cast<const float4*>(p.affine + (static_cast<size_t>(n) * C + c) * 2);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float4 t = ap[k];
+        a[2 * k] = t.x; b[2 * k] = t.y; a[2 * k + 1] = t.z; b[2 * k + 1] = t.w;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { a[k] = 1.f; b[k] = 0.f; }
+    }
+    float o[8];
+    if (p.resample == 1) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = 0.f;
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          float v[8];
+          load8(src + ((static_cast<size_t>(n) * p.Hi + 2 * yo + dy) * p.Wi + 2 * xo + dx) * Cs + cs, v);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            float t = a[k] * v[k] + b[k];
+            if (p.act) t = silu_f(t);
+            o[k] += t;
+          }
+        }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] *= 0.25f;
+    } else {
+      const int yi = p.resample == 2 ? (yo >> 1) : yo, xi = p.resample == 2 ? (xo >> 1) : xo;
+      float v[8];
+      load8(src + ((static_cast<size_t>(n) * p.Hi + yi) * p.Wi + xi) * Cs + cs, v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float t = a[k] * v[k] + b[k];
+        if (p.act) t = silu_f(t);
+        o[k] = t;
+      }
+    }
+    store8(p.out + ((static_cast<size_t>(n) * p.Ho + yo) * p.Wo + xo) * C + c, o);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// x_t fp32 NCHW [N][Cin][H][W] -> fp16 NHWC [N][H][W][64], channels >= Cin zero (conv_in operand)
+// ---------------------------------------------------------------------------------------------
+__global__ void pack_input_kernel(const float* __restrict__ x, __half* __restrict__ out, int N, int Cin, int H,
+                                  int W) {
+  const size_t total = static_cast<size_t>(N) * H * W * 8;  // 8 octets of 8 channels
+  for (size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int oc = static_cast<int>(idx & 7);
+    const size_t pix = idx >> 3;
+    const size_t hw = static_cast<size_t>(H) * W;
+    const size_t n = pix / hw, r = pix % hw;
+    float f[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = oc * 8 + k;
+      f[k] = c < Cin ? x[(n * Cin + c) * hw + r] : 0.f;
+    }
+    store8(out + pix * 64 + oc * 8, f);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Sinusoidal timestep embedding.  variant 0: DDPM [sin | cos], freq_i = exp(-i*ln(1e4)/(half-1))
+// (ddpm/diffusion.py:42-60); variant 1: ADM [cos | sin], freq_i = exp(-i*ln(1e4)/half) (improved_ddpm/nn.py:103-121)
+// ---------------------------------------------------------------------------------------------
+__global__ void timestep_embedding_kernel(const float* __restrict__ t, float* __restrict__ out, int N, int dim,
+                                          int variant) {
+  const int half = dim / 2;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < N * half; idx += gridDim.x * blockDim.x) {
+    const int n = idx / half, i = idx % half;
+    const float denom = variant == 0 ? static_cast<float>(half - 1) : static_cast<float>(half);
+    // same fp32 expression order as the reference: exp(arange * -(ln(1e4)/denom))
+    const float fr = variant == 0 ? expf(static_cast<float>(i) * -(logf(10000.0f) / denom))
+                                  : expf(-logf(10000.0f) * static_cast<float>(i) / denom);
+    const float a = t[n] * fr;
+    const float s = sinf(a), c = cosf(a);
+    out[n * dim + i] = variant == 0 ? s : c;
+    out[n * dim + half + i] = variant == 0 ? c : s;
+  }
+}
+
+// out[n][o] = bias[o] + sum_i W[o][i] * f(in[n][i]),  f = SiLU when act_in; one warp per (n, o)
+__global__ void linear_kernel(const float* __restrict__ in, int in_stride, const float* __restrict__ Wt,
+                              const float* __restrict__ bias, float* __restrict__ out, int out_stride, int N, int I,
+                              int O, int act_in, int act_out) {
+  const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp_global >= N * O) return;
+  const int n = warp_global / O, o = warp_global % O;
+  const float* x = in + static_cast<size_t>(n) * in_stride;
+  const float* w = Wt + static_cast<size_t>(o) * I;
+  float acc = 0.f;
+  for (int i = lane; i < I; i += 32) {
+    float v = x[i];
+    if (act_in) v = v / (1.0f + expf(-v));
+    acc += w[i] * v;
+  }
+  for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+  if (lane == 0) {
+    float r = acc + (bias ? bias[o] : 0.f);
+    if (act_out) r = r / (1.0f + expf(-r));
+    out[static_cast<size_t>(n) * out_stride + o] = r;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// DDIM update (utils/diffusion_utils.py:84-100), fp32, same operation order as the reference:
+//   x0   = (x - em*sqrt(1-at)) / sqrt(at)
+//   next = sqrt(an)*x0 + c2*et (+ c1*z)            c2 = sqrt(1-an) for eta=0
+// et / em are planar fp32 [N][Ce][H][W] of which channels [0,3) are epsilon (learn_sigma split :47-51).
+// ---------------------------------------------------------------------------------------------
+__global__ void ddim_update_kernel(const float* __restrict__ x, const float* __restrict__ et,
+                                   const float* __restrict__ em, const float* __restrict__ z,
+                                   float* __restrict__ x_next, float* __restrict__ x0_out, int N, int Cx, int Ce,
+                                   int HW, float at, float an, float c1, float c2, int use_z) {
+  const float sq1 = sqrtf(1.0f - at), sqa = sqrtf(at), sqn = sqrtf(an);
+  const size_t total = static_cast<size_t>(N) * Cx * HW;
+  for (size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t n = idx / (static_cast<size_t>(Cx) * HW), r = idx % (static_cast<size_t>(Cx) * HW);
+    const size_t eidx = n * Ce * HW + r;
+    const float e = et[eidx], m = em[eidx];
+    const float x0 = __fdiv_rn(__fsub_rn(x[idx], __fmul_rn(m, sq1)), sqa);
+    float nx = __fadd_rn(__fmul_rn(sqn, x0), __fmul_rn(c2, e));
+    if (use_z) nx = __fadd_rn(nx, __fmul_rn(c1, z[idx]));
+    x_next[idx] = nx;
+    if (x0_out) x0_out[idx] = x0;
+  }
+}
+
+}  // namespace asyrp
+
+using namespace asyrp;
+
+static inline int grid_for(size_t total, int block, int cap_mult = 8) {
+  size_t g = (total + block - 1) / block;
+  const size_t cap = static_cast<size_t>(sm_count() > 0 ? sm_count() : 148) * cap_mult;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return static_cast<int>(g);
+}
+
+extern "C" {
+
+ASYRP_API int asyrp_gn_finalize(const float* st_a, int Ca, int Ta, const float* st_b, int Cb, int Tb,
+                                const float* gamma, const float* beta, float eps, int N, int HW,
+                                const float* scale_shift, int ss_stride, float* affine, void* stream) {
+  const int C = Ca + Cb;
+  ASYRP_REQUIRE(C % 64 == 0, "asyrp_gn_finalize: C=%d must be a multiple of 64", C);
+  const float count = static_cast<float>(HW) * (C / 32);
+  gn_finalize_kernel<<<dim3(32, N), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      st_a, Ca, Ta, st_b, Cb, Tb, gamma, beta, eps, count, scale_shift, ss_stride, affine);
+  ASYRP_CHECK_CUDA(cudaGetLastError());
+  return ASYRP_OK;
+}
+
+ASYRP_API int asyrp_apply(const void* src_a, int Ca, const void* src_b, int Cb, const float* affine, void* out,
+                          int N, int Hi, int Wi, int act, int resample, void* stream) {
+  ASYRP_REQUIRE(Ca % 8 == 0 && Cb % 8 == 0, "asyrp_apply: channels must be multiples of 8");
+  ApplyParams p;
+  p.src_a = static_cast<const __half*>(src_a); p.Ca = Ca;
+  p.src_b = static_cast<const __half*>(src_b); p.Cb = Cb;
+  p.affine = affine; p.out = static_cast<__half*>(out);
+  p.N = N; p.Hi = Hi; p.Wi = Wi;
+  p.Ho = resample == 1 ? Hi / 2 : (resample == 2 ? Hi * 2 : Hi);
+  p.Wo = resample == 1 ? Wi / 2 : (resample == 2 ? Wi * 2 : Wi);
+  p.act = act; p.resample = resample;
+  const size_t total = static_cast<size_t>(N) * p.Ho * p.Wo * ((Ca + Cb) / 8);
+  apply_kernel<<<grid_for(total, 256, 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  ASYRP_CHECK_CUDA(cudaGetLastError());
+  return ASYRP_OK;
+}
+
+ASYRP_API int asyrp_pack_input(const float* x, void* out, int N, int Cin, int H, int W, void* stream) {
+  ASYRP_REQUIRE(Cin <= 64, "asyrp_pack_input: Cin=%d > 64", Cin);
+  const size_t total = static_cast<size_t>(N) * H * W * 8;
+  pack_input_kernel<<<grid_for(total, 256, 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, static_cast<__half*>(out), N, Cin, H, W);
+  ASYRP_CHECK_CUDA(cudaGetLastError());
+  return ASYRP_OK;
+}
+
+ASYRP_API int asyrp_timestep_embedding(const float* t, float* out, int N, int dim, int variant, void* stream) {
+  ASYRP_REQUIRE(dim % 2 == 0, "asyrp_timestep_embedding: odd dim %d", dim);
+  const int total = N * (dim / 2);
+  timestep_embedding_kernel<<<(total + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(t, out, N, dim,
+                                                                                               variant);
+  ASYRP_CHECK_CUDA(cudaGetLastError());
+  return ASYRP_OK;
+}
+
+ASYRP_API int asyrp_linear(const float* in, int in_stride, const float* W, const float* bias, float* out,
+                           int out_stride, int N, int I, int O, int act_in, int act_out, void* stream) {
+  const size_t warps = static_cast<size_t>(N) * O;
+  const int block = 256;
+  const int grid = static_cast<int>((warps * 32 + block - 1) / block);
+  linear_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(in, in_stride, W, bias, out, out_stride, N,
+                                                                      I, O, act_in, act_out);
+  ASYRP_CHECK_CUDA(cudaGetLastError());
+  return ASYRP_OK;
+}
+
+ASYRP_API int asyrp_ddim_update(const float* x, const float* et, const float* em, const float* z, float* x_next,
+                                float* x0_out, int N, int Cx, int Ce, int HW, float at, float an, float c1, float c2,
+                                void* stream) {
+  const size_t total = static_cast<size_t>(N) * Cx * HW;
+  ddim_update_kernel<<<grid_for(total, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, et, em, z, x_next, x0_out, N, Cx, Ce, HW, at, an, c1, c2, z != nullptr);
+  ASYRP_CHECK_CUDA(cudaGetLastError());
+  return ASYRP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,157 @@
+"""Python handles over the C-ABI entry points (include/asyrp_b200.h), operating on torch CUDA tensors.
+
+torch is used for device memory and streams only; every computation below is a kernel of
+libasyrp_b200.so.  Layout conventions: activations NHWC fp16, weights [Cout][taps*Cin] fp16 (tap-major),
+statistics / affine tables / embeddings / sampler state fp32.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import AsyrpConvDesc, check
+
+MODE_1x1, MODE_3x3, MODE_3x3_S2 = 0, 1, 2
+RESAMPLE_NONE, RESAMPLE_AVGPOOL2, RESAMPLE_UP2 = 0, 1, 2
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.AsyrpError("asyrp_official_b200 ops need CUDA tensors (there is no CPU path)")
+
+
+def pack_conv_weight(w):
+    """[O][I][kh][kw] (torch Conv2d) or [O][I] / [O][I][1] -> [O][kh*kw*I] fp16, tap-major / channel-minor."""
+    if w.dim() == 2:
+        w = w[:, :, None, None]
+    if w.dim() == 3:
+        w = w[:, :, :, None]
+    o = w.shape[0]
+    return w.permute(0, 2, 3, 1).reshape(o, -1).to(torch.float16).contiguous()
+
+
+def conv_stats_tiles(H, W):
+    return _lib.load().asyrp_conv_stats_tiles(H, W)
+
+
+def new_stats(N, H, W, C, device):
+    """Partial GroupNorm sums written by a conv epilogue: [N][tiles][C/2][2] fp32."""
+    return torch.zeros(N, conv_stats_tiles(H, W), C // 2, 2, dtype=torch.float32, device=device)
+
+
+class ConvOp:
+    """One implicit-GEMM convolution launch (asyrp_conv_create / asyrp_conv_launch).
+
+    segs: list of (src NHWC fp16 tensor, mode).  The output is [N][H][W][Cout]; for MODE_3x3_S2 the source is
+    [N][2H][2W][C].  weight: packed fp16 [Cout][K] ([N][Cout][K] when weight_batched).
+    """
+
+    def __init__(self, segs, weight, out=None, ebias=None, ebias_stride=0, residual=None, res_scale=1.0,
+                 acc_scale=1.0, stats=None, out_planar=None, out_shape=None, weight_batched=False):
+        lib = _lib.load()
+        srcs = [s for s, _ in segs]
+        _need_cuda(*srcs, weight, out, ebias, residual, stats, out_planar)
+        if out is not None:
+            N, H, W, Cout = out.shape
+        else:
+            N, H, W, Cout = out_shape
+        d = AsyrpConvDesc()
+        d.N, d.H, d.W, d.Cout = N, H, W, Cout
+        d.nseg = len(segs)
+        ktot = 0
+        for i, (src, mode) in enumerate(segs):
+            assert src.dtype == torch.float16 and src.is_contiguous()
+            d.seg[i].src = src.data_ptr()
+            d.seg[i].C = src.shape[-1]
+            d.seg[i].mode = mode
+            ktot += (1 if mode == MODE_1x1 else 9) * src.shape[-1]
+        assert weight.dtype == torch.float16 and weight.is_contiguous() and weight.shape[-1] == ktot, \
+            (weight.shape, ktot)
+        assert weight.shape[-2] == Cout
+        d.weight = weight.data_ptr()
+        d.weight_batched = int(weight_batched)
+        d.ebias = ebias.data_ptr() if ebias is not None else None
+        d.ebias_stride = ebias_stride
+        d.residual = residual.data_ptr() if residual is not None else None
+        d.res_scale, d.acc_scale = res_scale, acc_scale
+        d.out = out.data_ptr() if out is not None else None
+        d.stats = stats.data_ptr() if stats is not None else None
+        if out_planar is not None:
+            assert out_planar.dtype == torch.float32
+            d.out_planar = out_planar.data_ptr()
+            d.planar_c = out_planar.shape[1]
+        self._keep = (srcs, weight, out, ebias, residual, stats, out_planar)
+        h = C.c_void_p()
+        check(lib.asyrp_conv_create(C.byref(d), C.byref(h)), "asyrp_conv_create")
+        self._h = h
+        self._lib = lib
+
+    def launch(self):
+        check(self._lib.asyrp_conv_launch(self._h, _stream()), "asyrp_conv_launch")
+
+    __call__ = launch
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._lib.asyrp_conv_destroy(self._h)
+            self._h = None
+
+
+def gn_finalize(stats_a, Ca, stats_b, Cb, gamma, beta, eps, N, HW, affine, scale_shift=None, ss_stride=0):
+    lib = _lib.load()
+    Ta = stats_a.shape[1]
+    Tb = stats_b.shape[1] if stats_b is not None else 0
+    check(lib.asyrp_gn_finalize(_ptr(stats_a), Ca, Ta, _ptr(stats_b), Cb, Tb, _ptr(gamma), _ptr(beta), eps, N, HW,
+                                _ptr(scale_shift), ss_stride, _ptr(affine), _stream()), "asyrp_gn_finalize")
+
+
+def apply(src_a, src_b, affine, out, act, resample=RESAMPLE_NONE):
+    lib = _lib.load()
+    N, Hi, Wi, Ca = src_a.shape
+    Cb = src_b.shape[-1] if src_b is not None else 0
+    check(lib.asyrp_apply(_ptr(src_a), Ca, _ptr(src_b), Cb, _ptr(affine), _ptr(out), N, Hi, Wi, int(act),
+                          resample, _stream()), "asyrp_apply")
+
+
+def pack_input(x, out):
+    lib = _lib.load()
+    N, Cin, H, W = x.shape
+    check(lib.asyrp_pack_input(_ptr(x), _ptr(out), N, Cin, H, W, _stream()), "asyrp_pack_input")
+
+
+def timestep_embedding(t, out, variant):
+    lib = _lib.load()
+    N, dim = out.shape
+    check(lib.asyrp_timestep_embedding(_ptr(t), _ptr(out), N, dim, variant, _stream()), "asyrp_timestep_embedding")
+
+
+def linear(inp, weight, bias, out, act_in=False, act_out=False):
+    lib = _lib.load()
+    N, I = inp.shape
+    O = weight.shape[0]
+    assert weight.shape[1] == I and out.shape[1] >= O
+    check(lib.asyrp_linear(_ptr(inp), inp.stride(0), _ptr(weight), _ptr(bias), _ptr(out), out.stride(0), N, I, O,
+                           int(act_in), int(act_out), _stream()), "asyrp_linear")
+
+
+def ddim_update(x, et, em, z, x_next, x0_out, at, an, c1, c2):
+    lib = _lib.load()
+    N, Cx, H, W = x.shape
+    Ce = et.shape[1]
+    check(lib.asyrp_ddim_update(_ptr(x), _ptr(et), _ptr(em), _ptr(z), _ptr(x_next), _ptr(x0_out), N, Cx, Ce, H * W,
+                                at, an, c1, c2, _stream()), "asyrp_ddim_update")
+
+
+def attention(qkv, out, heads, head_dim, scale):
+    lib = _lib.load()
+    N, T, _ = qkv.shape
+    check(lib.asyrp_attention(_ptr(qkv), _ptr(out), N, T, heads, head_dim, scale, _stream()), "asyrp_attention")

@@ -1,0 +1,276 @@
+"""Kernel-level parity: every C-ABI op against a plain fp64/fp32 torch CPU evaluation of the same formula on
+the same fp16-rounded operands.  Tolerances are fp16-output rounding (2^-11 relative) plus fp32 accumulation
+order effects; stated per test."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    from asyrp_official_b200 import ops
+    return ops
+
+
+def _rand(shape, gen, scale=1.0):
+    return (torch.randn(shape, generator=gen) * scale)
+
+
+def _nhwc_half(x_nchw, dev):
+    return x_nchw.permute(0, 2, 3, 1).contiguous().to(torch.float16).to(dev)
+
+
+def _from_nhwc(t):
+    return t.float().cpu().permute(0, 3, 1, 2)
+
+
+def _h(x):
+    """fp16 rounding applied on the CPU reference side (the operands the kernel actually sees)"""
+    return x.to(torch.float16).double()
+
+
+def _check(out, ref, tol_rel, what):
+    err = (out.double() - ref).abs().max().item()
+    mag = ref.abs().max().item()
+    assert err <= tol_rel * mag + 1e-6, f"{what}: max-abs err {err:.3e} vs max|ref| {mag:.3e}"
+
+
+def _stats_ref(ref_nchw):
+    n, c, h, w = ref_nchw.shape
+    r = ref_nchw.reshape(n, c // 2, 2, h * w)
+    return torch.stack([r.sum(dim=(2, 3)), (r * r).sum(dim=(2, 3))], dim=-1)  # [N][C/2][2]
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout", [(2, 32, 32, 64, 64), (2, 32, 32, 128, 128), (1, 16, 48, 128, 256),
+                                            (3, 8, 8, 128, 128), (5, 4, 4, 64, 128), (2, 64, 64, 192, 192)])
+def test_conv3x3_bias_residual_stats(cuda_device, N, H, W, Cin, Cout):
+    ops = _ops()
+    g = torch.Generator().manual_seed(1)
+    x = _rand((N, Cin, H, W), g)
+    w = _rand((Cout, Cin, 3, 3), g, 1.0 / math.sqrt(9 * Cin))
+    eb = _rand((N, Cout), g)
+    res = _rand((N, Cout, H, W), g)
+    ref = F.conv2d(_h(x), _h(w), padding=1) + eb.double()[:, :, None, None]
+    ref = 0.75 * ref + 1.5 * _h(res)
+    out = torch.empty(N, H, W, Cout, dtype=torch.float16, device=cuda_device)
+    stats = ops.new_stats(N, H, W, Cout, cuda_device)
+    op = ops.ConvOp([(_nhwc_half(x, cuda_device), ops.MODE_3x3)], ops.pack_conv_weight(w).to(cuda_device), out=out,
+                    ebias=eb.to(cuda_device), ebias_stride=Cout, residual=_nhwc_half(res, cuda_device),
+                    res_scale=1.5, acc_scale=0.75, stats=stats)
+    op.launch()
+    op.launch()  # idempotent relaunch (persistent barriers re-initialised per launch)
+    torch.cuda.synchronize()
+    _check(_from_nhwc(out), ref, 1.5e-3, "conv3x3")
+    st = stats.sum(dim=1).cpu().double()
+    sref = _stats_ref(ref)
+    assert (st - sref).abs().max().item() <= 2e-3 * sref.abs().max().item() + 1e-3
+
+
+def test_conv1x1_concat_two_sources(cuda_device):
+    ops = _ops()
+    g = torch.Generator().manual_seed(2)
+    N, H, W, C1, C2, Cout = 2, 16, 16, 128, 64, 128
+    x1, x2 = _rand((N, C1, H, W), g), _rand((N, C2, H, W), g)
+    w = _rand((Cout, C1 + C2, 1, 1), g, 1.0 / math.sqrt(C1 + C2))
+    b = _rand((Cout,), g)
+    ref = F.conv2d(torch.cat([_h(x1), _h(x2)], 1), _h(w)) + b.double()[None, :, None, None]
+    out = torch.empty(N, H, W, Cout, dtype=torch.float16, device=cuda_device)
+    op = ops.ConvOp([(_nhwc_half(x1, cuda_device), ops.MODE_1x1), (_nhwc_half(x2, cuda_device), ops.MODE_1x1)],
+                    ops.pack_conv_weight(w).to(cuda_device), out=out, ebias=b.to(cuda_device))
+    op.launch()
+    torch.cuda.synchronize()
+    _check(_from_nhwc(out), ref, 1.5e-3, "conv1x1 concat")
+
+
+def test_conv3x3_with_fused_1x1_shortcut(cuda_device):
+    """conv2(a2) + nin_shortcut(cat(x1, x2)) accumulated in one TMEM tile (ddpm/diffusion.py:159-170)."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(3)
+    N, H, W, C1, C2, Cout = 2, 32, 32, 128, 64, 128
+    a2, x1, x2 = _rand((N, Cout, H, W), g), _rand((N, C1, H, W), g), _rand((N, C2, H, W), g)
+    w3 = _rand((Cout, Cout, 3, 3), g, 1.0 / math.sqrt(9 * Cout))
+    w1 = _rand((Cout, C1 + C2, 1, 1), g, 1.0 / math.sqrt(C1 + C2))
+    ref = F.conv2d(_h(a2), _h(w3), padding=1) + F.conv2d(torch.cat([_h(x1), _h(x2)], 1), _h(w1))
+    wp = torch.cat([ops.pack_conv_weight(w3), ops.pack_conv_weight(w1[:, :C1]), ops.pack_conv_weight(w1[:, C1:])], 1)
+    out = torch.empty(N, H, W, Cout, dtype=torch.float16, device=cuda_device)
+    op = ops.ConvOp([(_nhwc_half(a2, cuda_device), ops.MODE_3x3), (_nhwc_half(x1, cuda_device), ops.MODE_1x1),
+                     (_nhwc_half(x2, cuda_device), ops.MODE_1x1)], wp.contiguous().to(cuda_device), out=out)
+    op.launch()
+    torch.cuda.synchronize()
+    _check(_from_nhwc(out), ref, 1.5e-3, "conv3x3+shortcut")
+
+
+def test_conv3x3_stride2_asymmetric_pad(cuda_device):
+    """Downsample: pad (0,1,0,1) then 3x3 stride 2 (ddpm/diffusion.py:103-108)."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(4)
+    N, Hi, Wi, C = 2, 32, 32, 128
+    x = _rand((N, C, Hi, Wi), g)
+    w = _rand((C, C, 3, 3), g, 1.0 / math.sqrt(9 * C))
+    b = _rand((C,), g)
+    ref = F.conv2d(F.pad(_h(x), (0, 1, 0, 1)), _h(w), stride=2) + b.double()[None, :, None, None]
+    out = torch.empty(N, Hi // 2, Wi // 2, C, dtype=torch.float16, device=cuda_device)
+    op = ops.ConvOp([(_nhwc_half(x, cuda_device), ops.MODE_3x3_S2)], ops.pack_conv_weight(w).to(cuda_device),
+                    out=out, ebias=b.to(cuda_device))
+    op.launch()
+    torch.cuda.synchronize()
+    _check(_from_nhwc(out), ref, 1.5e-3, "conv3x3 s2")
+
+
+def test_conv_planar_fp32_output(cuda_device):
+    """conv_out: 3 (or 6) real output channels written as fp32 NCHW (ddpm/diffusion.py:424-428)."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(5)
+    N, H, W, C, Co = 2, 32, 32, 128, 6
+    x = _rand((N, C, H, W), g)
+    w = torch.zeros(64, C, 3, 3)
+    w[:Co] = _rand((Co, C, 3, 3), g, 1.0 / math.sqrt(9 * C))
+    b = torch.zeros(64)
+    b[:Co] = _rand((Co,), g)
+    ref = F.conv2d(_h(x), _h(w[:Co]), padding=1) + b[:Co].double()[None, :, None, None]
+    outp = torch.zeros(N, Co, H, W, dtype=torch.float32, device=cuda_device)
+    op = ops.ConvOp([(_nhwc_half(x, cuda_device), ops.MODE_3x3)], ops.pack_conv_weight(w).to(cuda_device),
+                    out_shape=(N, H, W, 64), ebias=b.to(cuda_device), out_planar=outp)
+    op.launch()
+    torch.cuda.synchronize()
+    _check(outp.cpu(), ref, 2e-5, "planar fp32")
+
+
+def test_batched_gemm_mode(cuda_device):
+    """H=1 'image' rows x per-sample weight matrix: logits = q k^T as used by a tensor-core attention."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(6)
+    N, T, D = 3, 256, 128
+    q, k = _rand((N, T, D), g), _rand((N, T, D), g)
+    ref = torch.einsum("ntd,nsd->nts", _h(q), _h(k))
+    out = torch.empty(N, 1, T, T, dtype=torch.float16, device=cuda_device)
+    op = ops.ConvOp([(q.to(torch.float16).to(cuda_device).reshape(N, 1, T, D), ops.MODE_1x1)],
+                    k.to(torch.float16).to(cuda_device).contiguous(), out=out, weight_batched=True)
+    op.launch()
+    torch.cuda.synchronize()
+    _check(out.float().cpu().reshape(N, T, T), ref, 1.5e-3, "batched gemm")
+
+
+@pytest.mark.parametrize("Ca,Cb,resample,act", [(128, 0, 0, 1), (128, 64, 0, 1), (64, 128, 0, 0), (128, 0, 1, 1),
+                                                (128, 0, 2, 1), (64, 0, 2, 0)])
+def test_groupnorm_finalize_and_apply(cuda_device, Ca, Cb, resample, act):
+    """GroupNorm(32) over a (possibly concatenated) tensor from conv-epilogue partial sums, then
+    SiLU / avg-pool / nearest-up.  The statistics come from a real conv epilogue (1x1 identity-free conv)."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(7)
+    N, H, W = 2, 16, 16
+    C = Ca + Cb
+    srcs, stats, refs = [], [], []
+    for Cs in [c for c in (Ca, Cb) if c]:
+        xin = _rand((N, 64, H, W), g)
+        w = _rand((Cs, 64, 1, 1), g, 0.2)
+        b = _rand((Cs,), g)
+        out = torch.empty(N, H, W, Cs, dtype=torch.float16, device=cuda_device)
+        st = ops.new_stats(N, H, W, Cs, cuda_device)
+        ops.ConvOp([(_nhwc_half(xin, cuda_device), ops.MODE_1x1)], ops.pack_conv_weight(w).to(cuda_device), out=out,
+                   ebias=b.to(cuda_device), stats=st).launch()
+        srcs.append(out)
+        stats.append(st)
+        refs.append(F.conv2d(_h(xin), _h(w)) + b.double()[None, :, None, None])
+    torch.cuda.synchronize()
+    xcat = torch.cat([_from_nhwc(s).double() for s in srcs], 1)  # what apply actually reads (fp16-rounded)
+    gamma, beta = _rand((C,), g) + 1.0, _rand((C,), g)
+    ss = _rand((N, 2 * C), g, 0.3)
+    eps = 1e-6
+    # statistics are taken on the fp32 pre-rounding values
+    xstat = torch.cat(refs, 1)
+    xg = xstat.reshape(N, 32, -1)
+    mean, var = xg.mean(-1), xg.var(-1, unbiased=False)
+    cpg = C // 32
+    mean_c = mean.repeat_interleave(cpg, 1)[:, :, None, None]
+    rstd_c = (1.0 / torch.sqrt(var + eps)).repeat_interleave(cpg, 1)[:, :, None, None]
+    y = (xcat - mean_c) * rstd_c * gamma.double()[None, :, None, None] + beta.double()[None, :, None, None]
+    y = y * (1 + ss[:, :C].double()[:, :, None, None]) + ss[:, C:].double()[:, :, None, None]
+    if act:
+        y = y * torch.sigmoid(y)
+    if resample == 1:
+        y = F.avg_pool2d(y, 2)
+    elif resample == 2:
+        y = F.interpolate(y, scale_factor=2, mode="nearest")
+    affine = torch.empty(N, C, 2, dtype=torch.float32, device=cuda_device)
+    ops.gn_finalize(stats[0], Ca, stats[1] if Cb else None, Cb, gamma.to(cuda_device), beta.to(cuda_device), eps, N,
+                    H * W, affine, scale_shift=ss.to(cuda_device), ss_stride=2 * C)
+    Ho, Wo = y.shape[2:]
+    out = torch.empty(N, Ho, Wo, C, dtype=torch.float16, device=cuda_device)
+    ops.apply(srcs[0], srcs[1] if Cb else None, affine, out, act, resample)
+    torch.cuda.synchronize()
+    _check(_from_nhwc(out), y, 2e-3, "gn+apply")
+
+
+@pytest.mark.parametrize("N,T,heads,D", [(2, 256, 1, 512), (2, 64, 1, 256), (1, 1024, 8, 64), (3, 200, 2, 128)])
+def test_attention(cuda_device, N, T, heads, D):
+    ops = _ops()
+    g = torch.Generator().manual_seed(8)
+    C = heads * D
+    qkv = _rand((N, T, 3 * C), g)
+    qh = _h(qkv)
+    q, k, v = [qh[:, :, i * C:(i + 1) * C].reshape(N, T, heads, D).permute(0, 2, 1, 3) for i in range(3)]
+    scale = D ** -0.5
+    p = torch.softmax(q @ k.transpose(-1, -2) * scale, dim=-1)
+    ref = (p @ v).permute(0, 2, 1, 3).reshape(N, T, C)
+    out = torch.empty(N, T, C, dtype=torch.float16, device=cuda_device)
+    ops.attention(qkv.to(torch.float16).to(cuda_device), out, heads, D, scale)
+    torch.cuda.synchronize()
+    _check(out.float().cpu(), ref, 1.5e-3, "attention")
+
+
+def test_pack_embedding_linear_ddim(cuda_device):
+    ops = _ops()
+    g = torch.Generator().manual_seed(9)
+    dev = cuda_device
+    # pack_input
+    x = _rand((2, 3, 16, 16), g)
+    packed = torch.empty(2, 16, 16, 64, dtype=torch.float16, device=dev)
+    ops.pack_input(x.to(dev), packed)
+    ref = torch.zeros(2, 16, 16, 64)
+    ref[..., :3] = x.permute(0, 2, 3, 1).to(torch.float16).float()
+    assert torch.equal(packed.float().cpu(), ref)
+    # timestep embeddings, both conventions
+    t = torch.tensor([999.0, 512.0, 25.0, 0.0])
+    for variant, dim in ((0, 128), (1, 256)):
+        half = dim // 2
+        if variant == 0:
+            fr = torch.exp(torch.arange(half, dtype=torch.float32) * -(math.log(10000) / (half - 1)))
+            e = t[:, None] * fr[None]
+            ref = torch.cat([torch.sin(e), torch.cos(e)], 1)
+        else:
+            fr = torch.exp(-math.log(10000) * torch.arange(half, dtype=torch.float32) / half)
+            e = t[:, None] * fr[None]
+            ref = torch.cat([torch.cos(e), torch.sin(e)], 1)
+        out = torch.empty(4, dim, dtype=torch.float32, device=dev)
+        ops.timestep_embedding(t.to(dev), out, variant)
+        assert (out.cpu() - ref).abs().max().item() < 2e-4  # sin/cos of arguments up to ~1e3 in fp32
+    # linear with SiLU on the input / output
+    inp, w, b = _rand((4, 96), g), _rand((40, 96), g, 0.1), _rand((40,), g)
+    out = torch.empty(4, 40, dtype=torch.float32, device=dev)
+    ops.linear(inp.to(dev), w.to(dev), b.to(dev), out, act_in=True)
+    ref = F.silu(inp.double()) @ w.double().t() + b.double()
+    assert (out.cpu().double() - ref).abs().max().item() < 1e-5
+    ops.linear(inp.to(dev), w.to(dev), b.to(dev), out, act_out=True)
+    ref = F.silu(inp.double() @ w.double().t() + b.double())
+    assert (out.cpu().double() - ref).abs().max().item() < 1e-5
+    # DDIM update, eta = 0 and eta > 0 (utils/diffusion_utils.py:84-97), fp32 op order as the reference
+    xt, et, em, z = (_rand((2, 3, 8, 8), g) for _ in range(4))
+    et6 = torch.cat([et, _rand((2, 3, 8, 8), g)], 1)
+    em6 = torch.cat([em, _rand((2, 3, 8, 8), g)], 1)
+    at, an = torch.tensor(0.3, dtype=torch.float32), torch.tensor(0.6, dtype=torch.float32)
+    x0 = (xt - em * (1 - at).sqrt()) / at.sqrt()
+    nxt0 = an.sqrt() * x0 + (1 - an).sqrt() * et
+    c1 = 1.0 * ((1 - at / an) * (1 - an) / (1 - at)).sqrt()
+    c2 = ((1 - an) - c1 ** 2).sqrt()
+    nxt1 = an.sqrt() * x0 + c2 * et + c1 * z
+    o_next, o_x0 = torch.empty(2, 3, 8, 8, device=dev), torch.empty(2, 3, 8, 8, device=dev)
+    ops.ddim_update(xt.to(dev), et6.to(dev), em6.to(dev), None, o_next, o_x0, at.item(), an.item(), 0.0,
+                    (1 - an).sqrt().item())
+    assert torch.equal(o_x0.cpu(), x0) and torch.equal(o_next.cpu(), nxt0)
+    ops.ddim_update(xt.to(dev), et6.to(dev), em6.to(dev), z.to(dev), o_next, o_x0, at.item(), an.item(), c1.item(),
+                    c2.item())
+    assert (o_next.cpu() - nxt1).abs().max().item() <= 1e-6
