@@ -40,6 +40,7 @@ SIGNATURES = {
     "asyrp_conv_stats_tiles": (c_int, [c_int, c_int]),
     "asyrp_conv_create": (c_int, [C.POINTER(AsyrpConvDesc), C.POINTER(c_void_p)]),
     "asyrp_conv_launch": (c_int, [c_void_p, c_void_p]),
+    "asyrp_conv_set_scales": (c_int, [c_void_p, c_float, c_float]),
     "asyrp_conv_destroy": (None, [c_void_p]),
     "asyrp_gn_finalize": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_float,
                                   c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
@@ -51,6 +52,8 @@ SIGNATURES = {
                              c_int, c_void_p]),
     "asyrp_ddim_update": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                   c_int, c_float, c_float, c_float, c_float, c_void_p]),
+    "asyrp_axpby": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_float, C.c_longlong, c_void_p]),
+    "asyrp_unpack_nchw": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "asyrp_attention": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p]),
 }
 

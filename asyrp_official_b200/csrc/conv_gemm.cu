@@ -524,6 +524,16 @@ ASYRP_API int asyrp_conv_launch(void* handle, void* stream) {
   return ASYRP_OK;
 }
 
+// h2 = c0*h + c_i*delta_h_i (ddpm/diffusion.py:512-516) is evaluated by the last DeltaBlock conv's epilogue;
+// the coefficients are per-call arguments of the reference forward(), hence adjustable after creation.
+ASYRP_API int asyrp_conv_set_scales(void* handle, float acc_scale, float res_scale) {
+  ASYRP_REQUIRE(handle, "asyrp_conv_set_scales: null op");
+  ConvOp* op = static_cast<ConvOp*>(handle);
+  op->p.acc_scale = acc_scale;
+  op->p.res_scale = res_scale;
+  return ASYRP_OK;
+}
+
 ASYRP_API void asyrp_conv_destroy(void* handle) { delete static_cast<ConvOp*>(handle); }
 
 }  // extern "C"

@@ -262,6 +262,31 @@ __global__ void ddim_update_kernel(const float* __restrict__ x, const float* __r
   }
 }
 
+// out = alpha*a + beta*b on fp16 tensors (fp32 math): h2 = c0*h + c_i*delta_h_i  (ddpm/diffusion.py:512-516)
+__global__ void axpby_kernel(const __half* __restrict__ a, const __half* __restrict__ b, __half* __restrict__ out,
+                             float alpha, float beta, size_t n8) {
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    float fa[8], fb[8], o[8];
+    load8(a + i * 8, fa);
+    load8(b + i * 8, fb);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = alpha * fa[k] + beta * fb[k];
+    store8(out + i * 8, o);
+  }
+}
+
+// NHWC fp16 -> NCHW fp32 (API-visible copies of delta_h / middle_h)
+__global__ void unpack_nchw_kernel(const __half* __restrict__ in, float* __restrict__ out, int N, int C, int HW) {
+  const size_t total = static_cast<size_t>(N) * C * HW;
+  for (size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t n = idx / (static_cast<size_t>(C) * HW), r = idx % (static_cast<size_t>(C) * HW);
+    const size_t c = r / HW, p = r % HW;
+    out[idx] = __half2float(in[(n * HW + p) * C + c]);
+  }
+}
+
 }  // namespace asyrp
 
 using namespace asyrp;
@@ -340,6 +365,24 @@ ASYRP_API int asyrp_ddim_update(const float* x, const float* et, const float* em
   const size_t total = static_cast<size_t>(N) * Cx * HW;
   ddim_update_kernel<<<grid_for(total, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       x, et, em, z, x_next, x0_out, N, Cx, Ce, HW, at, an, c1, c2, z != nullptr);
+  ASYRP_CHECK_CUDA(cudaGetLastError());
+  return ASYRP_OK;
+}
+
+ASYRP_API int asyrp_axpby(const void* a, const void* b, void* out, float alpha, float beta, long long numel,
+                          void* stream) {
+  ASYRP_REQUIRE(numel % 8 == 0, "asyrp_axpby: numel must be a multiple of 8");
+  const size_t n8 = static_cast<size_t>(numel) / 8;
+  axpby_kernel<<<grid_for(n8, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(a), static_cast<const __half*>(b), static_cast<__half*>(out), alpha, beta, n8);
+  ASYRP_CHECK_CUDA(cudaGetLastError());
+  return ASYRP_OK;
+}
+
+ASYRP_API int asyrp_unpack_nchw(const void* in, float* out, int N, int C, int HW, void* stream) {
+  const size_t total = static_cast<size_t>(N) * C * HW;
+  unpack_nchw_kernel<<<grid_for(total, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(in), out, N, C, HW);
   ASYRP_CHECK_CUDA(cudaGetLastError());
   return ASYRP_OK;
 }

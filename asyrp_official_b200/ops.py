@@ -100,6 +100,9 @@ class ConvOp:
 
     __call__ = launch
 
+    def set_scales(self, acc_scale, res_scale):
+        check(self._lib.asyrp_conv_set_scales(self._h, acc_scale, res_scale), "asyrp_conv_set_scales")
+
     def __del__(self):
         if getattr(self, "_h", None):
             self._lib.asyrp_conv_destroy(self._h)
@@ -155,3 +158,15 @@ def attention(qkv, out, heads, head_dim, scale):
     lib = _lib.load()
     N, T, _ = qkv.shape
     check(lib.asyrp_attention(_ptr(qkv), _ptr(out), N, T, heads, head_dim, scale, _stream()), "asyrp_attention")
+
+
+def axpby(a, b, out, alpha, beta):
+    lib = _lib.load()
+    check(lib.asyrp_axpby(_ptr(a), _ptr(b), _ptr(out), alpha, beta, a.numel(), _stream()), "asyrp_axpby")
+
+
+def unpack_nchw(inp, out):
+    """NHWC fp16 -> NCHW fp32"""
+    lib = _lib.load()
+    N, H, W, Cc = inp.shape
+    check(lib.asyrp_unpack_nchw(_ptr(inp), _ptr(out), N, Cc, H * W, _stream()), "asyrp_unpack_nchw")

@@ -1,0 +1,211 @@
+"""Generate the golden fixtures under tests/golden/ by running the REFERENCE'S OWN modules (imported from
+/root/reference, which only exists in the build container) on the synthetic weights of oracle/synth.py.
+
+    python tests/golden/make_golden.py [--full]
+
+The fixtures pin the oracle (tests/test_oracle.py, CPU) and are what the CUDA engine is compared with on the GPU
+box, where /root/reference does not exist.  Nothing here is imported by the product package.
+
+Fixtures (npz, fp32):
+  ddpm_mini.npz / adm_mini.npz      full tensors of reduced configurations: plain forward, Asyrp forward
+                                    (t >= t_edit and t < t_edit), 10-step edit trajectory with a stochastic tail
+  ddpm_celeba_fwd.npz               CelebA-HQ config, 256x256, B=1, Asyrp forward at t=999 (stride-4 subsample)
+  ddpm_celeba_traj40.npz            40-step Asyrp edit trajectory, B=1 (stride-4 subsample of x_0 + per-step |x0_t| max)
+  adm_afhq_fwd.npz, adm_imagenet_fwd.npz   one Asyrp forward each (stride-4 subsample)
+"""
+import argparse
+import os
+import sys
+import time
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = "/root/reference"
+sys.path.insert(0, ROOT)
+sys.path.insert(0, REF)
+
+from oracle import adm as o_adm, ddpm as o_ddpm, sampler as o_smp, synth  # noqa: E402
+
+from models.ddpm.diffusion import DDPM  # noqa: E402  (reference)
+from models.improved_ddpm.unet import UNetModel  # noqa: E402  (reference)
+from models.improved_ddpm.script_util import i_DDPM  # noqa: E402  (reference)
+import utils.diffusion_utils as ref_du  # noqa: E402  (reference)
+
+
+def ref_ddpm(cfg, n_delta):
+    c = SimpleNamespace(model=SimpleNamespace(ch=cfg["ch"], out_ch=cfg["out_ch"], ch_mult=list(cfg["ch_mult"]),
+                                              num_res_blocks=cfg["num_res_blocks"],
+                                              attn_resolutions=list(cfg["attn_resolutions"]), dropout=0.0,
+                                              in_channels=cfg["in_channels"], resamp_with_conv=True),
+                        data=SimpleNamespace(image_size=cfg["image_size"]))
+    m = DDPM(c)
+    m.setattr_layers(n_delta)
+    return m.eval()
+
+
+def ref_adm(hp, n_delta):
+    ds = tuple(hp["image_size"] // r for r in hp["attention_resolutions"])
+    m = UNetModel(image_size=hp["image_size"], in_channels=3, model_channels=hp["model_channels"],
+                  out_channels=hp["out_channels"], num_res_blocks=hp["num_res_blocks"], attention_resolutions=ds,
+                  dropout=0.0, channel_mult=hp["channel_mult"], num_classes=None, use_checkpoint=False,
+                  use_fp16=False, num_heads=4, num_head_channels=hp["num_head_channels"], num_heads_upsample=-1,
+                  use_scale_shift_norm=True, resblock_updown=True, use_new_attention_order=False)
+    m.setattr_layers(n_delta)
+    return m.eval()
+
+
+def load_checked(model, shapes, sd, ignore=()):
+    """the oracle's parameter inventory must equal the reference module's state_dict (names and shapes)"""
+    ref_sd = {k: tuple(v.shape) for k, v in model.state_dict().items() if not k.startswith(tuple(ignore))}
+    mine = {k: tuple(v) for k, v in shapes.items()}
+    assert ref_sd == mine, (sorted(set(ref_sd) ^ set(mine))[:10],
+                            [(k, ref_sd[k], mine[k]) for k in ref_sd if k in mine and ref_sd[k] != mine[k]][:10])
+    res = model.load_state_dict(sd, strict=False)
+    assert not res.unexpected_keys and all(k.startswith(tuple(ignore)) for k in res.missing_keys), res
+
+
+def ref_trajectory(model, x_T, betas, seq, seq_next, t_edit, t_addnoise, learn_sigma, noises, rec):
+    """diffusion_latent.py:499-520 with the reference denoising_step; randn_like replaced by the pre-drawn noise"""
+    x = x_T.clone()
+    bs = x.shape[0]
+    for i, j in zip(reversed(seq), reversed(seq_next)):
+        t = torch.ones(bs) * i
+        t_next = torch.ones(bs) * j
+        orig = torch.randn_like
+        ref_du.torch.randn_like = lambda ten, _i=i: noises[_i]
+        try:
+            x, x0_t, _, _ = ref_du.denoising_step(x, t=t, t_next=t_next, models=model, logvars=None if learn_sigma else
+                                                  o_smp.make_logvar(o_smp.get_beta_schedule(
+                                                      beta_start=1e-4, beta_end=0.02, num_diffusion_timesteps=1000)),
+                                                  sampling_type="ddim", b=betas, learn_sigma=learn_sigma, index=0,
+                                                  eta=1.0 if i < t_addnoise else 0.0, t_edit=t_edit,
+                                                  hs_coeff=(1.0, 1.0), delta_h=None, ignore_timestep=False,
+                                                  dt_lambda=1, warigari=False)
+        finally:
+            ref_du.torch.randn_like = orig
+        rec.append((i, x0_t))
+    return x
+
+
+def sub(t, s=4):
+    return t[..., ::s, ::s].contiguous().numpy()
+
+
+@torch.no_grad()
+def mini(family):
+    if family == "ddpm":
+        cfg = o_ddpm.MINI_CFG
+        shapes = o_ddpm.ddpm_param_shapes(cfg, 1)
+        model = ref_ddpm(cfg, 1)
+        fwd = lambda sd, *a, **k: o_ddpm.ddpm_forward(sd, cfg, *a, **k)  # noqa: E731
+        learn_sigma = False
+    else:
+        cfg = o_adm.MINI_HP
+        shapes = o_adm.adm_param_shapes(cfg, 1)
+        model = ref_adm(cfg, 1)
+        fwd = lambda sd, *a, **k: o_adm.adm_forward(sd, cfg, *a, **k)  # noqa: E731
+        learn_sigma = True
+    sd = synth.synth_state_dict(shapes, seed=1234, style="jittered")
+    load_checked(model, shapes, sd)
+    B, S = 2, cfg["image_size"]
+    x = synth.synth_noise((B, 3, S, S), seed=1234)
+    out = {}
+    # plain forward (index=None), Asyrp forward above and below t_edit
+    cases = {"plain": dict(t=999.0), "edit": dict(t=600.0, index=0, t_edit=500, hs_coeff=(1.0, 0.7)),
+             "pass": dict(t=300.0, index=0, t_edit=500, hs_coeff=(1.0, 0.7))}
+    for name, kw in cases.items():
+        kw = dict(kw)
+        t = torch.ones(B) * kw.pop("t")
+        r = model(x, t, **kw)
+        o = fwd(sd, x, t, **kw)
+        for key, a, b in zip(("et", "et_mod", "delta_h", "middle_h"), r, o):
+            if a is None:
+                assert b is None
+                continue
+            assert torch.equal(a, b), f"oracle != reference: {family} {name} {key} {(a - b).abs().max()}"
+            out[f"{name}_{key}"] = a.numpy()
+    # 10-step trajectory, t_edit=500, stochastic (eta=1) below t_addnoise=300
+    betas = o_smp.make_betas()
+    seq, seq_next = o_smp.make_sequences(999, 10)
+    g = torch.Generator().manual_seed(4321)
+    noises = {i: torch.randn(x.shape, generator=g) for i in seq}
+    rec = []
+    xf = ref_trajectory(model, x, betas, seq, seq_next, 500, 300, learn_sigma, noises, rec)
+    rec_o = []
+    xo = o_smp.run_trajectory(lambda *a, **k: fwd(sd, *a, **k), x, betas=betas, seq=seq, seq_next=seq_next,
+                              t_edit=500, t_addnoise=300, index=0, hs_coeff=(1.0, 1.0), learn_sigma=learn_sigma,
+                              noises=noises, record=rec_o)
+    assert torch.equal(xf, xo), (xf - xo).abs().max()
+    out["traj_x0"] = xf.numpy()
+    out["traj_x0t"] = np.stack([r[1].numpy() for r in rec])
+    out["traj_noise_seed"] = np.array(4321)
+    np.savez_compressed(os.path.join(HERE, f"{family}_mini.npz"), **out)
+    print(f"{family}_mini ok: |x_final|max={xf.abs().max():.3f}")
+
+
+@torch.no_grad()
+def full_forward(name, family, cfg, t_val=999.0):
+    t0 = time.time()
+    if family == "ddpm":
+        shapes = o_ddpm.ddpm_param_shapes(cfg, 1)
+        model = ref_ddpm(cfg, 1)
+        fwd = lambda sd, *a, **k: o_ddpm.ddpm_forward(sd, cfg, *a, **k)  # noqa: E731
+        ignore = ()
+    else:
+        shapes = o_adm.adm_param_shapes(cfg, 1)
+        model = ref_adm(cfg, 1)
+        fwd = lambda sd, *a, **k: o_adm.adm_forward(sd, cfg, *a, **k)  # noqa: E731
+        ignore = ()
+    sd = synth.synth_state_dict(shapes, seed=1234, style="torch_default")
+    load_checked(model, shapes, sd, ignore)
+    x = synth.synth_noise((1, 3, 256, 256), seed=1234)
+    t = torch.ones(1) * t_val
+    r = model(x, t, index=0, t_edit=500, hs_coeff=(1.0, 1.0))
+    o = fwd(sd, x, t, index=0, t_edit=500, hs_coeff=(1.0, 1.0))
+    out = {}
+    for key, a, b in zip(("et", "et_mod", "delta_h", "middle_h"), r, o):
+        assert torch.equal(a, b), f"oracle != reference: {name} {key} {(a - b).abs().max()}"
+        out[key] = sub(a) if a.shape[-1] == 256 else a.numpy()
+        out[key + "_absmax"] = np.array(a.abs().max().item())
+        out[key + "_mean"] = np.array(a.double().mean().item())
+        out[key + "_std"] = np.array(a.double().std().item())
+    np.savez_compressed(os.path.join(HERE, f"{name}_fwd.npz"), **out)
+    print(f"{name}_fwd ok ({time.time() - t0:.1f}s): |et|max={r[0].abs().max():.3f} |et_mod|max={r[1].abs().max():.3f}")
+    return model, sd
+
+
+@torch.no_grad()
+def full_trajectory(model, sd, cfg):
+    """BASELINE config 2 restricted to B=1: DDPM CelebA-HQ 256x256, 40-step Asyrp edit, t_edit=500, t_addnoise=200"""
+    t0 = time.time()
+    x = synth.synth_noise((1, 3, 256, 256), seed=1234)
+    betas = o_smp.make_betas()
+    seq, seq_next = o_smp.make_sequences(999, 40)
+    g = torch.Generator().manual_seed(4321)
+    noises = {i: torch.randn(x.shape, generator=g) for i in seq}
+    rec = []
+    xf = ref_trajectory(model, x, betas, seq, seq_next, 500, 200, False, noises, rec)
+    out = {"x0": sub(xf), "x0_absmax": np.array(xf.abs().max().item()), "x0_std": np.array(xf.double().std().item()),
+           "x0t_absmax": np.array([r[1].abs().max().item() for r in rec]),
+           "x0_full_f16": xf.to(torch.float16).numpy()}
+    np.savez_compressed(os.path.join(HERE, "ddpm_celeba_traj40.npz"), **out)
+    print(f"ddpm_celeba_traj40 ok ({time.time() - t0:.1f}s): |x_0|max={xf.abs().max():.2f}")
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--full", action="store_true", help="also the 256x256 fixtures (minutes of CPU time)")
+    args = ap.parse_args()
+    torch.set_num_threads(os.cpu_count())
+    mini("ddpm")
+    mini("adm")
+    if args.full:
+        m, sd = full_forward("ddpm_celeba", "ddpm", o_ddpm.CELEBA_CFG)
+        full_trajectory(m, sd, o_ddpm.CELEBA_CFG)
+        del m, sd
+        full_forward("adm_afhq", "adm", o_adm.AFHQ_HP)
+        full_forward("adm_imagenet", "adm", o_adm.IMAGENET_HP)
