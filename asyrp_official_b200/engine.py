@@ -1,0 +1,554 @@
+"""UNet kernel plans and the trajectory engine.
+
+A `UNetEngine` owns, for one UNet (arch.Arch + a state dict in the reference's naming):
+  * the packed device weights (fp16 [Cout][K] conv matrices, fp32 biases / norm parameters, fused 1x1 shortcut
+    columns, concatenated timestep-embedding projections);
+  * one static kernel plan per batch size: pre-created conv ops (TMA descriptors), pooled activation buffers and
+    an ordered list of kernel launches for the shared encoder, the Δh injection, and the two decoder passes
+    (reference forward: models/ddpm/diffusion.py:473-580, models/improved_ddpm/unet.py:676-752);
+  * `forward()` — the reference's per-call semantics — and `sample()` — the whole N-step Asyrp trajectory
+    (diffusion_latent.py:499-520 + utils/diffusion_utils.py:24-109) captured once into a CUDA graph and replayed
+    with no host synchronisation between steps.
+
+Everything computed here is a kernel of libasyrp_b200.so; torch provides device memory, streams and graphs.
+"""
+import math
+
+import torch
+
+from . import ops
+from .arch import Arch, Attn, Res, Resample
+from .ops import MODE_1x1, MODE_3x3, MODE_3x3_S2, RESAMPLE_AVGPOOL2, RESAMPLE_NONE, RESAMPLE_UP2
+
+
+class Act:
+    """NHWC fp16 activation + the partial GroupNorm sums its producer wrote"""
+    __slots__ = ("t", "stats")
+
+    def __init__(self, t, stats=None):
+        self.t, self.stats = t, stats
+
+    @property
+    def C(self):
+        return self.t.shape[3]
+
+    @property
+    def H(self):
+        return self.t.shape[1]
+
+    @property
+    def W(self):
+        return self.t.shape[2]
+
+
+class Pool:
+    """Exact-size free lists of device buffers.  The plan is a fixed launch sequence on one stream, so a buffer
+    released after the last op that reads it can be handed to any later op."""
+
+    def __init__(self, device):
+        self.device = device
+        self.free = {}
+        self.total = 0
+
+    def alloc(self, shape, dtype):
+        n = math.prod(shape) * torch.empty((), dtype=dtype).element_size()
+        n = (n + 255) // 256 * 256
+        lst = self.free.get(n)
+        if lst:
+            raw = lst.pop()
+        else:
+            raw = torch.empty(n, dtype=torch.uint8, device=self.device)
+            self.total += n
+        t = raw[: math.prod(shape) * torch.empty((), dtype=dtype).element_size()].view(dtype).view(shape)
+        t._asyrp_raw = raw
+        return t
+
+    def release(self, t):
+        raw = t._asyrp_raw
+        self.free.setdefault(raw.numel(), []).append(raw)
+
+
+def pack_weights(arch: Arch, sd, device, n_delta):
+    """reference-named fp32 state dict -> device tensors the plan consumes"""
+    W = {}
+    f32 = lambda t: t.detach().to(device=device, dtype=torch.float32).contiguous()  # noqa: E731
+    pk = lambda t: ops.pack_conv_weight(t.detach().float()).to(device)  # noqa: E731
+    ddpm = arch.family == "ddpm"
+
+    # timestep MLP
+    for n in arch.temb_names:
+        W[n + ".weight"], W[n + ".bias"] = f32(sd[n + ".weight"]), f32(sd[n + ".bias"])
+
+    # conv_in: input channels padded to one 64-channel K chunk
+    w = sd[arch.conv_in + ".weight"].detach().float()
+    wpad = torch.zeros(w.shape[0], 64, 3, 3)
+    wpad[:, : w.shape[1]] = w.cpu()
+    W["conv_in.w"], W["conv_in.b"] = pk(wpad), f32(sd[arch.conv_in + ".bias"])
+
+    emb_w, emb_b, emb_off = [], [], {}
+    off = 0
+
+    def add_emb(name, w_, b_):
+        nonlocal off
+        emb_w.append(w_.detach().float().cpu())
+        emb_b.append(b_.detach().float().cpu())
+        emb_off[name] = off
+        off += w_.shape[0]
+
+    def res(layer):
+        p = layer.name
+        if ddpm:
+            n1, c1, n2, c2, sc = ".norm1", ".conv1", ".norm2", ".conv2", ".nin_shortcut"
+            # conv1 bias folded into the timestep projection row: h = conv1(..) + b1 + temb_proj(swish(temb))
+            add_emb(p, sd[p + ".temb_proj.weight"], sd[p + ".temb_proj.bias"] + sd[p + c1 + ".bias"])
+        else:
+            n1, c1, n2, c2, sc = ".in_layers.0", ".in_layers.2", ".out_layers.0", ".out_layers.3", ".skip_connection"
+            add_emb(p, sd[p + ".emb_layers.1.weight"], sd[p + ".emb_layers.1.bias"])
+            W[p + ".b1"] = f32(sd[p + c1 + ".bias"])
+        W[p + ".g1"], W[p + ".be1"] = f32(sd[p + n1 + ".weight"]), f32(sd[p + n1 + ".bias"])
+        W[p + ".g2"], W[p + ".be2"] = f32(sd[p + n2 + ".weight"]), f32(sd[p + n2 + ".bias"])
+        W[p + ".w1"] = pk(sd[p + c1 + ".weight"])
+        w2 = ops.pack_conv_weight(sd[p + c2 + ".weight"].detach().float())
+        b2 = sd[p + c2 + ".bias"].detach().float().cpu()
+        if layer.cin != layer.cout:
+            # 1x1 shortcut on the raw (possibly concatenated) input: extra K columns of the same GEMM
+            w2 = torch.cat([w2, ops.pack_conv_weight(sd[p + sc + ".weight"].detach().float())], dim=1)
+            b2 = b2 + sd[p + sc + ".bias"].detach().float().cpu()
+        W[p + ".w2"], W[p + ".b2"] = w2.contiguous().to(device), f32(b2)
+
+    def attn(layer):
+        p, c = layer.name, layer.c
+        W[p + ".g"], W[p + ".be"] = f32(sd[p + ".norm.weight"]), f32(sd[p + ".norm.bias"])
+        if ddpm:
+            wq = torch.cat([sd[p + f".{n}.weight"].detach().float().reshape(c, c) for n in ("q", "k", "v")], 0)
+            bq = torch.cat([sd[p + f".{n}.bias"].detach().float() for n in ("q", "k", "v")], 0)
+        else:
+            # reference channel order [head][q|k|v][ch] (QKVAttentionLegacy, unet.py:386-388) -> [q|k|v][head][ch]
+            d = arch.head_ch
+            heads = c // d
+            wq = sd[p + ".qkv.weight"].detach().float().reshape(heads, 3, d, c).permute(1, 0, 2, 3).reshape(3 * c, c)
+            bq = sd[p + ".qkv.bias"].detach().float().reshape(heads, 3, d).permute(1, 0, 2).reshape(3 * c)
+        W[p + ".wqkv"], W[p + ".bqkv"] = pk(wq), f32(bq)
+        W[p + ".wproj"] = pk(sd[p + ".proj_out.weight"].detach().float().reshape(c, c))
+        W[p + ".bproj"] = f32(sd[p + ".proj_out.bias"])
+
+    def resample(layer):
+        p = layer.name
+        W[p + ".w"], W[p + ".b"] = pk(sd[p + ".conv.weight"]), f32(sd[p + ".conv.bias"])
+
+    for stage in arch.enc + [arch.mid] + arch.dec:
+        for layer in stage:
+            {Res: res, Attn: attn, Resample: resample}[type(layer)](layer)
+
+    # conv_out: output channels padded to one 64-wide N tile; only [0, out_ch) is stored (fp32 planar)
+    w = sd[arch.conv_out + ".weight"].detach().float().cpu()
+    wpad = torch.zeros(64, *w.shape[1:])
+    wpad[: w.shape[0]] = w
+    bpad = torch.zeros(64)
+    bpad[: w.shape[0]] = sd[arch.conv_out + ".bias"].detach().float().cpu()
+    W["conv_out.w"], W["conv_out.b"] = pk(wpad), f32(bpad)
+    W["norm_out.g"], W["norm_out.be"] = f32(sd[arch.norm_out + ".weight"]), f32(sd[arch.norm_out + ".bias"])
+
+    # DeltaBlocks  (ddpm/diffusion.py:228-263, improved_ddpm/unet.py:776-853)
+    for i in range(n_delta):
+        p = f"layer_{i}"
+        if ddpm:
+            W[p + ".w1"] = pk(sd[p + ".conv1.weight"])
+            W[p + ".b1"] = f32(sd[p + ".conv1.bias"])
+            add_emb(p, sd[p + ".temb_proj.weight"], sd[p + ".temb_proj.bias"] + sd[p + ".conv1.bias"])
+            W[p + ".g2"], W[p + ".be2"] = f32(sd[p + ".norm2.weight"]), f32(sd[p + ".norm2.bias"])
+            W[p + ".w2"], W[p + ".b2"] = pk(sd[p + ".conv2.weight"]), f32(sd[p + ".conv2.bias"])
+        else:
+            W[p + ".g1"], W[p + ".be1"] = f32(sd[p + ".in_layers.0.weight"]), f32(sd[p + ".in_layers.0.bias"])
+            W[p + ".w1"] = pk(sd[p + ".in_layers.2.weight"])
+            W[p + ".b1"] = f32(sd[p + ".in_layers.2.bias"])
+            add_emb(p, sd[p + ".emb_layers.1.weight"], sd[p + ".emb_layers.1.bias"] + sd[p + ".in_layers.2.bias"])
+            W[p + ".g2"], W[p + ".be2"] = f32(sd[p + ".out_layers.0.weight"]), f32(sd[p + ".out_layers.0.bias"])
+            W[p + ".w2"], W[p + ".b2"] = pk(sd[p + ".out_layers.3.weight"]), f32(sd[p + ".out_layers.3.bias"])
+
+    W["emb_cat.w"] = torch.cat(emb_w, 0).to(device).contiguous()
+    W["emb_cat.b"] = torch.cat(emb_b, 0).to(device).contiguous()
+    return W, emb_off, off
+
+
+class Plan:
+    """Static launch sequence for one batch size"""
+
+    def __init__(self, eng, N):
+        self.eng, self.N = eng, N
+        a, dev = eng.arch, eng.device
+        S = a.image_size
+        self.pool = Pool(dev)
+        self.x = torch.zeros(N, a.in_ch, S, S, dtype=torch.float32, device=dev)  # sampler state / UNet input
+        self.t = torch.zeros(N, dtype=torch.float32, device=dev)
+        self.et = torch.zeros(N, a.out_ch, S, S, dtype=torch.float32, device=dev)
+        self.et_mod = torch.zeros(N, a.out_ch, S, S, dtype=torch.float32, device=dev)
+        self.enc_ops, self.delta_ops, self.dec_ops, self.dec_mod_ops = [], [], [], []
+        self.scale_ops = []  # conv ops whose epilogue scales are hs_coeff
+        self._cur = self.enc_ops
+        self._build()
+
+    # ------------------------------------------------------------------ builder primitives
+    def _emit(self, fn):
+        self._cur.append(fn)
+
+    def _act(self, H, W, C, stats=True):
+        t = self.pool.alloc((self.N, H, W, C), torch.float16)
+        st = None
+        if stats:
+            st = self.pool.alloc((self.N, ops.conv_stats_tiles(H, W), C // 2, 2), torch.float32)
+        return Act(t, st)
+
+    def _free(self, act):
+        self.pool.release(act.t)
+        if act.stats is not None:
+            self.pool.release(act.stats)
+
+    def _gn(self, srcs, gamma, beta, scale_shift=None, ss_stride=0):
+        N = self.N
+        C = sum(s.C for s in srcs)
+        aff = self.pool.alloc((N, C, 2), torch.float32)
+        a, b = srcs[0], (srcs[1] if len(srcs) > 1 else None)
+        HW = a.H * a.W
+        eps = self.eng.arch.gn_eps
+        self._emit(lambda: ops.gn_finalize(a.stats, a.C, b.stats if b else None, b.C if b else 0, gamma, beta, eps, N,
+                                           HW, aff, scale_shift, ss_stride))
+        return aff
+
+    def _apply(self, srcs, affine, act, resample=RESAMPLE_NONE):
+        a, b = srcs[0], (srcs[1] if len(srcs) > 1 else None)
+        C = sum(s.C for s in srcs)
+        H = a.H // 2 if resample == RESAMPLE_AVGPOOL2 else (a.H * 2 if resample == RESAMPLE_UP2 else a.H)
+        Wd = a.W // 2 if resample == RESAMPLE_AVGPOOL2 else (a.W * 2 if resample == RESAMPLE_UP2 else a.W)
+        out = self._act(H, Wd, C, stats=False)
+        self._emit(lambda: ops.apply(a.t, b.t if b else None, affine, out.t, act, resample))
+        return out
+
+    def _conv(self, segs, weight, Cout, H, W, ebias=None, ebias_stride=0, residual=None, res_scale=1.0,
+              acc_scale=1.0, stats=True, planar=None):
+        out = None
+        if planar is None:
+            out = self._act(H, W, Cout, stats=stats)
+        op = ops.ConvOp([(s.t, m) for s, m in segs], weight, out=out.t if out else None, ebias=ebias,
+                        ebias_stride=ebias_stride, residual=residual.t if residual is not None else None,
+                        res_scale=res_scale, acc_scale=acc_scale, stats=out.stats if out else None,
+                        out_planar=planar, out_shape=(self.N, H, W, Cout))
+        self._emit(op.launch)
+        return out, op
+
+    # ------------------------------------------------------------------ blocks
+    def _res_block(self, layer: Res, srcs):
+        eng, W = self.eng, self.eng.W
+        p, ddpm = layer.name, self.eng.arch.family == "ddpm"
+        eoff = eng.emb_off[p]
+        mode = {"none": RESAMPLE_NONE, "up": RESAMPLE_UP2, "down": RESAMPLE_AVGPOOL2}[layer.resample]
+        aff1 = self._gn(srcs, W[p + ".g1"], W[p + ".be1"])
+        a1 = self._apply(srcs, aff1, 1, mode)
+        self.pool.release(aff1)
+        xr = None
+        if mode != RESAMPLE_NONE:  # ADM up/down block resamples the skip branch too (unet.py:279-284)
+            xr = self._apply(srcs, None, 0, mode)
+        H, Wd = a1.H, a1.W
+        if ddpm:
+            h, _ = self._conv([(a1, MODE_3x3)], W[p + ".w1"], layer.cout, H, Wd,
+                              ebias=self.emb_all[:, eoff:eoff + layer.cout], ebias_stride=eng.emb_total)
+            self._free(a1)
+            aff2 = self._gn([h], W[p + ".g2"], W[p + ".be2"])
+        else:
+            h, _ = self._conv([(a1, MODE_3x3)], W[p + ".w1"], layer.cout, H, Wd, ebias=W[p + ".b1"])
+            self._free(a1)
+            # GN(h)*(1+scale)+shift, [scale | shift] = Linear(SiLU(emb))  (unet.py:287-294)
+            aff2 = self._gn([h], W[p + ".g2"], W[p + ".be2"], self.emb_all[:, eoff:eoff + 2 * layer.cout],
+                            eng.emb_total)
+        a2 = self._apply([h], aff2, 1)
+        self.pool.release(aff2)
+        self._free(h)
+        if layer.cin != layer.cout:
+            segs = [(a2, MODE_3x3)] + [(s, MODE_1x1) for s in srcs]
+            out, _ = self._conv(segs, W[p + ".w2"], layer.cout, H, Wd, ebias=W[p + ".b2"])
+        else:
+            resid = xr if xr is not None else srcs[0]
+            out, _ = self._conv([(a2, MODE_3x3)], W[p + ".w2"], layer.cout, H, Wd, ebias=W[p + ".b2"], residual=resid)
+        self._free(a2)
+        if xr is not None:
+            self._free(xr)
+        return out
+
+    def _attn_block(self, layer: Attn, x):
+        a_, W = self.eng.arch, self.eng.W
+        p, C = layer.name, layer.c
+        d = a_.head_ch if a_.head_ch else C
+        heads = C // d
+        aff = self._gn([x], W[p + ".g"], W[p + ".be"])
+        xn = self._apply([x], aff, 0)
+        self.pool.release(aff)
+        qkv, _ = self._conv([(xn, MODE_1x1)], W[p + ".wqkv"], 3 * C, x.H, x.W, ebias=W[p + ".bqkv"], stats=False)
+        self._free(xn)
+        att = self._act(x.H, x.W, C, stats=False)
+        N, T = self.N, x.H * x.W
+        scale = float(d) ** -0.5  # C^-0.5 (ddpm/diffusion.py:213) == (d^-1/4)^2 (improved_ddpm/unet.py:389-392)
+        self._emit(lambda: ops.attention(qkv.t.view(N, T, 3 * C), att.t.view(N, T, C), heads, d, scale))
+        out, _ = self._conv([(att, MODE_1x1)], W[p + ".wproj"], C, x.H, x.W, ebias=W[p + ".bproj"], residual=x)
+        self._free(qkv)
+        self._free(att)
+        return out
+
+    def _resample_block(self, layer: Resample, x):
+        W = self.eng.W
+        p = layer.name
+        if layer.kind == "down":
+            out, _ = self._conv([(x, MODE_3x3_S2)], W[p + ".w"], layer.c, x.H // 2, x.W // 2, ebias=W[p + ".b"])
+            return out
+        up = self._apply([x], None, 0, RESAMPLE_UP2)
+        out, _ = self._conv([(up, MODE_3x3)], W[p + ".w"], layer.c, up.H, up.W, ebias=W[p + ".b"])
+        self._free(up)
+        return out
+
+    def _run_stage(self, stage, h, skip=None, keep_input=False):
+        """apply the layers of one stage; intermediate tensors are returned to the pool"""
+        first = True
+        for layer in stage:
+            if isinstance(layer, Res):
+                srcs = [h, skip] if (first and skip is not None) else [h]
+                nh = self._res_block(layer, srcs)
+            elif isinstance(layer, Attn):
+                nh = self._attn_block(layer, h)
+            else:
+                nh = self._resample_block(layer, h)
+            if not (first and keep_input):
+                self._free(h)
+            h, first = nh, False
+        return h
+
+    # ------------------------------------------------------------------ whole network
+    def _build(self):
+        eng, a, N, dev = self.eng, self.eng.arch, self.N, self.eng.device
+        W = eng.W
+        S = a.image_size
+        # ---- timestep embedding MLP + every per-block projection in one launch each
+        self._cur = self.enc_ops
+        e0 = torch.zeros(N, a.base_ch, dtype=torch.float32, device=dev)
+        e1 = torch.zeros(N, a.temb_ch, dtype=torch.float32, device=dev)
+        self.temb = torch.zeros(N, a.temb_ch, dtype=torch.float32, device=dev)
+        self.emb_all = torch.zeros(N, eng.emb_total, dtype=torch.float32, device=dev)
+        variant = 0 if a.family == "ddpm" else 1
+        n0, n1 = a.temb_names
+        self._emit(lambda: ops.timestep_embedding(self.t, e0, variant))
+        self._emit(lambda: ops.linear(e0, W[n0 + ".weight"], W[n0 + ".bias"], e1, act_out=True))
+        self._emit(lambda: ops.linear(e1, W[n1 + ".weight"], W[n1 + ".bias"], self.temb))
+        self._emit(lambda: ops.linear(self.temb, W["emb_cat.w"], W["emb_cat.b"], self.emb_all, act_in=True))
+        # ---- encoder
+        xin = self._act(S, S, 64, stats=False)
+        self._emit(lambda: ops.pack_input(self.x, xin.t))
+        first_ch = a.enc[1][0].cin
+        h, _ = self._conv([(xin, MODE_3x3)], W["conv_in.w"], first_ch, S, S, ebias=W["conv_in.b"])
+        self._free(xin)
+        hs = [h]
+        for stage in a.enc[1:]:
+            h = self._run_stage(stage, hs[-1], keep_input=True)
+            hs.append(h)
+        h = self._run_stage(a.mid, hs[-1], keep_input=True)
+        self.middle_h = h
+        self.hs = hs
+        # ---- Δh injection: h2 = c0*h + sum_i c_{i+1} * layer_i(h, temb)
+        self._cur = self.delta_ops
+        self.delta_h = None
+        h2 = h
+        for i in range(eng.n_delta):
+            h2 = self._delta_block(i, h, h2, last=(i == eng.n_delta - 1))
+        self.h2 = h2
+        # ---- decoders: (h2 -> et_mod) and (h -> et); same weights, same skip tensors
+        if eng.n_delta:
+            self._cur = self.dec_mod_ops
+            self._decoder(self.h2, self.et_mod)
+        self._cur = self.dec_ops
+        self._decoder(self.middle_h, self.et)
+        self.mid_f32 = torch.zeros(N, a.mid_ch, h.H, h.W, dtype=torch.float32, device=dev)
+        self.delta_f32 = torch.zeros_like(self.mid_f32)
+
+    def _delta_block(self, i, h, h2_prev, last):
+        eng, a, W = self.eng, self.eng.arch, self.eng.W
+        p, C = f"layer_{i}", a.mid_ch
+        eoff = eng.emb_off[p]
+        src = h
+        if a.family == "adm":  # GN, SiLU before the first 1x1 conv (improved_ddpm/unet.py:821-825)
+            aff = self._gn([h], W[p + ".g1"], W[p + ".be1"])
+            src = self._apply([h], aff, 1)
+            self.pool.release(aff)
+        # two variants of the first conv: with the timestep projection (default) and without (ignore_timestep)
+        d1, op_t = self._conv([(src, MODE_1x1)], W[p + ".w1"], C, h.H, h.W,
+                              ebias=self.emb_all[:, eoff:eoff + C], ebias_stride=eng.emb_total)
+        self._cur.pop()
+        op_nt = ops.ConvOp([(src.t, MODE_1x1)], W[p + ".w1"], out=d1.t, ebias=W[p + ".b1"], stats=d1.stats)
+        st = self.eng.state
+        self._emit(lambda: (op_nt if st["ignore_timestep"] else op_t).launch())
+        if src is not h:
+            self._free(src)
+        aff = self._gn([d1], W[p + ".g2"], W[p + ".be2"])
+        a2 = self._apply([d1], aff, 1)
+        self.pool.release(aff)
+        self._free(d1)
+        if last:  # API-visible delta_h = output of the last DeltaBlock
+            dh, _ = self._conv([(a2, MODE_1x1)], W[p + ".w2"], C, h.H, h.W, ebias=W[p + ".b2"], stats=False)
+            self.delta_h = dh
+        # h2 = c_{i+1} * (conv2(a2) + b2) + (c0*h | 1*h2_prev), with GroupNorm partial sums for the decoder
+        h2, op = self._conv([(a2, MODE_1x1)], W[p + ".w2"], C, h.H, h.W, ebias=W[p + ".b2"], residual=h2_prev)
+        self.scale_ops.append((op, i))
+        self._free(a2)
+        if h2_prev is not h:
+            self._free(h2_prev)
+        return h2
+
+    def _decoder(self, h_in, out_planar):
+        a, W = self.eng.arch, self.eng.W
+        h = h_in
+        idx = -1
+        for si, stage in enumerate(a.dec):
+            h = self._run_stage(stage, h, skip=self.hs[idx], keep_input=(si == 0))
+            idx -= 1
+        aff = self._gn([h], W["norm_out.g"], W["norm_out.be"])
+        an = self._apply([h], aff, 1)
+        self.pool.release(aff)
+        self._free(h)
+        self._conv([(an, MODE_3x3)], W["conv_out.w"], 64, an.H, an.W, ebias=W["conv_out.b"], stats=False,
+                   planar=out_planar)
+        self._free(an)
+
+    # ------------------------------------------------------------------ execution
+    def set_coeffs(self, hs_coeff):
+        for op, i in self.scale_ops:
+            op.set_scales(float(hs_coeff[i + 1]), float(hs_coeff[0]) if i == 0 else 1.0)
+
+    def run_encoder(self):
+        for f in self.enc_ops:
+            f()
+
+    def run_edit(self):
+        for f in self.delta_ops:
+            f()
+        for f in self.dec_mod_ops:
+            f()
+
+    def run_decoder(self):
+        for f in self.dec_ops:
+            f()
+
+
+class UNetEngine:
+    """Device weights + plans for one UNet."""
+
+    def __init__(self, arch: Arch, state_dict, device, n_delta=0):
+        if not torch.cuda.is_available():
+            raise ops._lib.AsyrpError("UNetEngine needs a CUDA device (sm_100a); there is no CPU path")
+        ops._lib.load()
+        self.arch, self.device, self.n_delta = arch, torch.device(device), n_delta
+        self.state = {"ignore_timestep": False}
+        with torch.cuda.device(self.device):
+            self.W, self.emb_off, self.emb_total = pack_weights(arch, state_dict, self.device, n_delta)
+        self.plans = {}
+        self.graphs = {}
+
+    def plan(self, N) -> Plan:
+        if N not in self.plans:
+            with torch.cuda.device(self.device):
+                self.plans[N] = Plan(self, N)
+        return self.plans[N]
+
+    # ---- reference forward() semantics -------------------------------------------------------------
+    def forward(self, x, t, index=None, t_edit=400, hs_coeff=(1.0, 1.0), ignore_timestep=False):
+        """(et, et_modified | None, delta_h | None, middle_h) as fp32 NCHW tensors (new tensors, like the reference)."""
+        N = x.shape[0]
+        P = self.plan(N)
+        with torch.cuda.device(self.device):
+            P.x.copy_(x)
+            P.t.copy_(t.to(torch.float32))
+            edit = index is not None and float(t[0]) >= t_edit  # host decision, ddpm/diffusion.py:510
+            if index is not None and index + 1 > self.n_delta and edit:
+                raise ops._lib.AsyrpError(f"index={index} needs {index + 1} DeltaBlocks; engine packed {self.n_delta}")
+            self.state["ignore_timestep"] = bool(ignore_timestep)
+            P.run_encoder()
+            delta = None
+            if edit:
+                if index + 1 != self.n_delta:
+                    raise ops._lib.AsyrpError("forward(index=i) requires i+1 == number of packed DeltaBlocks")
+                P.set_coeffs(hs_coeff)
+                P.run_edit()
+                ops.unpack_nchw(P.delta_h.t, P.delta_f32)
+                delta = P.delta_f32.clone()
+            P.run_decoder()
+            ops.unpack_nchw(P.middle_h.t, P.mid_f32)
+            et = P.et.clone()
+            if index is None:
+                et_mod = None
+            elif edit:
+                et_mod = P.et_mod.clone()
+            else:
+                et_mod = et.clone()  # h2 = h below t_edit: the reference's second decoder pass is bit-identical
+            return et, et_mod, delta, P.mid_f32.clone()
+
+    # ---- whole trajectory --------------------------------------------------------------------------
+    def sample(self, x_T, schedule, noise=None, use_graph=True, out=None):
+        """Run the reverse trajectory of `schedule` (sampler.Schedule) from x_T; returns x_0 (fp32 NCHW).
+
+        The step list, the edit/plain/stochastic phase of every step and all coefficients are host-side integers /
+        floats fixed before launch, so the whole loop is one CUDA graph: per step a t-table copy, the UNet kernels,
+        and the fused DDIM update that writes x_t in place.  noise: [n_stochastic_steps][N][C][H][W] (pre-drawn)."""
+        N = x_T.shape[0]
+        P = self.plan(N)
+        key = (N, schedule.key())
+        with torch.cuda.device(self.device):
+            steps = schedule.steps
+            n_sto = sum(1 for s in steps if s.c1 != 0.0)
+            if n_sto:
+                assert noise is not None and noise.shape[0] == n_sto, "pre-drawn noise required for eta>0 steps"
+            g = self.graphs.get(key)
+            if g is None:
+                t_table = torch.tensor([[float(s.t)] * N for s in steps], dtype=torch.float32, device=self.device)
+                zbuf = torch.zeros((max(n_sto, 1), *P.x.shape), dtype=torch.float32, device=self.device)
+                P.set_coeffs(schedule.hs_coeff)
+                self.state["ignore_timestep"] = False
+
+                def body():
+                    zi = 0
+                    for k, s in enumerate(steps):
+                        P.t.copy_(t_table[k])
+                        P.run_encoder()
+                        edit = s.edit and self.n_delta > 0
+                        if edit:
+                            P.run_edit()
+                        P.run_decoder()
+                        z = None
+                        if s.c1 != 0.0:
+                            z = zbuf[zi]
+                            zi += 1
+                        ops.ddim_update(P.x, P.et, P.et_mod if edit else P.et, z, P.x, None, s.at, s.an, s.c1, s.c2)
+
+                g = {"zbuf": zbuf, "t_table": t_table, "body": body, "graph": None}
+                if use_graph:
+                    P.x.copy_(x_T)
+                    s_ = torch.cuda.Stream(device=self.device)
+                    s_.wait_stream(torch.cuda.current_stream())
+                    with torch.cuda.stream(s_):
+                        # warm-up launch outside capture (lazy function attributes, first-touch)
+                        P.t.copy_(t_table[0])
+                        P.run_encoder()
+                        P.run_edit() if self.n_delta else None
+                        P.run_decoder()
+                    torch.cuda.current_stream().wait_stream(s_)
+                    torch.cuda.synchronize(self.device)
+                    cg = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(cg):
+                        body()
+                    g["graph"] = cg
+                self.graphs[key] = g
+            P.x.copy_(x_T)
+            if n_sto:
+                g["zbuf"].copy_(noise)
+            if g["graph"] is not None:
+                g["graph"].replay()
+            else:
+                g["body"]()
+            if out is None:
+                return P.x.clone()
+            out.copy_(P.x)
+            return out

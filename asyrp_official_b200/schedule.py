@@ -1,0 +1,63 @@
+"""Host-side schedule of one Asyrp reverse trajectory.
+
+Everything the reference decides per step with device->host synchronisations — `t[0] >= t_edit`
+(models/ddpm/diffusion.py:510), `t[0] < t_addnoise` (diffusion_latent.py:513), `t_next.sum() == -bs`
+(utils/diffusion_utils.py:68) and the alpha-bar lookups (:66-71) — is an integer/float decision made here, once,
+before the trajectory graph is captured.
+"""
+from dataclasses import dataclass
+from typing import List, Tuple
+
+import numpy as np
+import torch
+
+
+@dataclass(frozen=True)
+class Step:
+    t: int
+    t_next: int
+    edit: bool     # t >= t_edit: DeltaBlock injection + second decoder pass
+    at: float      # alpha-bar_t       (fp32 value)
+    an: float      # alpha-bar_t_next  (1.0 when t_next == -1)
+    c1: float      # coefficient of the injected noise (0 for eta = 0)
+    c2: float      # coefficient of e_t: sqrt(1-an) for eta = 0
+
+
+def make_sequences(t_0=999, n_step=40):
+    """seq_test, seq_test_next  (diffusion_latent.py:570-574)"""
+    seq = [int(s + 1e-6) for s in list(np.linspace(0, 1, n_step) * t_0)]
+    return seq, [-1] + list(seq[:-1])
+
+
+class Schedule:
+    def __init__(self, betas, seq, seq_next, t_edit, t_addnoise=0, hs_coeff=(1.0, 1.0), edit=True):
+        """betas: fp32 tensor (Asyrp.betas).  Coefficients are evaluated with the same fp32 torch expressions as
+        utils/diffusion_utils.py:66-97 (cumprod in fp32 on the host) so that they are bit-identical to the CPU oracle."""
+        b = torch.as_tensor(betas, dtype=torch.float32).cpu()
+        ac = (1.0 - b).cumprod(dim=0)
+        steps: List[Step] = []
+        for i, j in zip(reversed(seq), reversed(seq_next)):
+            at = ac[i]
+            an = torch.ones_like(at) if j == -1 else ac[j]
+            eta = 1.0 if i < t_addnoise else 0.0
+            if eta == 0.0:
+                c1 = torch.zeros_like(at)
+                c2 = (1 - an).sqrt()
+            else:
+                c1 = eta * ((1 - at / an) * (1 - an) / (1 - at)).sqrt()
+                c2 = ((1 - an) - c1 ** 2).sqrt()
+            steps.append(Step(int(i), int(j), bool(edit and i >= t_edit), float(at), float(an), float(c1), float(c2)))
+        self.steps = steps
+        self.hs_coeff: Tuple[float, ...] = tuple(float(c) for c in hs_coeff)
+        self.t_edit, self.t_addnoise = t_edit, t_addnoise
+
+    def key(self):
+        return (tuple(self.steps), self.hs_coeff)
+
+    @property
+    def n_stochastic(self):
+        return sum(1 for s in self.steps if s.c1 != 0.0)
+
+    @property
+    def n_edit(self):
+        return sum(1 for s in self.steps if s.edit)
