@@ -1,0 +1,292 @@
+"""`Asyrp` runner — inference/editing half of the reference's diffusion_latent.py on the B200 engine.
+
+Mirrors, with the same attribute / flag names:
+  Asyrp.__init__               diffusion_latent.py:32-73    betas, logvar tables
+  Asyrp.load_pretrained_model  :76-126                      dataset -> UNet family dispatch, load_state_dict(strict=False)
+  Asyrp.run_test               :547-874                     sequences, Δh checkpoint, hs_coeff (single / multi-attribute /
+                                                            interpolation sweep), batching of latents
+  Asyrp.save_image             :445-544                     the reverse loops + PNG grid
+  Asyrp.random_noise_pairs     :1087-1188                   x_T = N(0,1) per image
+  Asyrp.set_t_edit_t_addnoise  :1308-1416                   user-defined values or LPIPS-table lookup given a cosine
+
+Differences (documented in INTEGRATION.md): the reverse loop is UNetEngine.sample() — one CUDA graph per
+(batch, schedule) instead of 40 Python iterations; pretrained weights come from --model_path (no URL download);
+CLIP is not available, so t_edit / t_addnoise come from --user_defined_t_edit/_t_addnoise or from the shipped
+LPIPS tables with an explicit --clip_cosine.  With torch.distributed initialised (one process per GPU) the image
+batches are sharded round-robin across ranks; the only collective is the initial weight broadcast.
+"""
+import os
+import time
+
+import numpy as np
+import torch
+
+from .modules import DDPM, guided_Diffusion, i_DDPM
+from .schedule import Schedule
+from .utils.diffusion_utils import get_beta_schedule
+
+
+class Asyrp(object):
+    def __init__(self, args, config, device=None):
+        self.args = args
+        self.config = config
+        if device is None:
+            device = torch.device("cuda") if torch.cuda.is_available() else torch.device("cpu")
+        self.device = torch.device(device)
+        self.model_var_type = config.model.var_type
+        betas = get_beta_schedule(beta_start=config.diffusion.beta_start, beta_end=config.diffusion.beta_end,
+                                  num_diffusion_timesteps=config.diffusion.num_diffusion_timesteps)
+        self.betas = torch.from_numpy(betas).float().to(self.device)
+        self.num_timesteps = betas.shape[0]
+        alphas = 1.0 - betas
+        alphas_cumprod = np.cumprod(alphas, axis=0)
+        alphas_cumprod_prev = np.append(1.0, alphas_cumprod[:-1])
+        posterior_variance = betas * (1.0 - alphas_cumprod_prev) / (1.0 - alphas_cumprod)
+        self.alphas_cumprod = alphas_cumprod
+        if self.model_var_type == "fixedlarge":
+            self.logvar = np.log(np.append(posterior_variance[1], betas[1:]))
+        elif self.model_var_type == 'fixedsmall':
+            self.logvar = np.log(np.maximum(posterior_variance, 1e-20))
+        self.learn_sigma = False  # set by load_pretrained_model()
+        self.t_edit = getattr(args, "user_defined_t_edit", None)
+        self.t_addnoise = getattr(args, "user_defined_t_addnoise", None)
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    # ------------------------------------------------------------------------------------------
+    def load_pretrained_model(self):
+        ds = self.config.data.dataset
+        if ds in ["CelebA_HQ", "LSUN", "CelebA_HQ_Dialog", "CUSTOM"]:
+            model = DDPM(self.config)
+            self.learn_sigma = False
+        elif ds in ["FFHQ", "AFHQ", "IMAGENET"]:
+            model = i_DDPM(ds)
+            self.learn_sigma = True
+        elif ds in ["MetFACE", "CelebA_HQ_P2"]:
+            model = guided_Diffusion(ds)
+            self.learn_sigma = True
+        else:
+            raise ValueError(f'Not implemented dataset {ds}')
+        path = getattr(self.args, "model_path", None)
+        if path:
+            ckpt = torch.load(path, map_location="cpu", weights_only=True)
+            model.load_state_dict(ckpt, strict=False)
+        elif getattr(self.args, "synthetic_weights", False):
+            from .synthetic import randomize_
+            randomize_(model, seed=getattr(self.args, "seed", 1234))
+        else:
+            raise FileNotFoundError("no --model_path given: pretrained UNet weights cannot be downloaded here "
+                                    "(pass --model_path <state dict> or --synthetic_weights)")
+        return model
+
+    # ------------------------------------------------------------------------------------------
+    def set_t_edit_t_addnoise(self, LPIPS_th=0.33, LPIPS_addnoise_th=0.1, return_clip_loss=False, cosine=None):
+        """t_edit = first t with LPIPS(x0_t, x0) >= LPIPS_th * cosine; t_addnoise = first t with LPIPS >= LPIPS_addnoise_th
+        on the x_t table (--add_noise_from_xt) or the same x0_t table (diffusion_latent.py:1331-1410).  Each of
+        --user_defined_t_edit / --user_defined_t_addnoise overrides its value.  The cosine is CLIP's text-direction
+        similarity in the reference (:1319-1329); CLIP is unavailable offline, so it is the explicit --clip_cosine.
+        Tables: <lpips_table_dir>/<config stem>_LPIPS_distance_{x0_t,x}.tsv (the reference ships them under utils/)."""
+        a = self.args
+        ut, ua = getattr(a, "user_defined_t_edit", None), getattr(a, "user_defined_t_addnoise", None)
+        if ut is not None and ua is not None:
+            self.t_edit, self.t_addnoise = ut, ua
+            return cosine if cosine is not None else getattr(a, "clip_cosine", None)
+        cosine = cosine if cosine is not None else getattr(a, "clip_cosine", None)
+        tdir = getattr(a, "lpips_table_dir", None) or "utils"
+        name = str(getattr(a, "config", "") or "").split(".")[0] or self.config.data.category
+        name = os.path.basename(name)
+        if name == "custom":
+            name = getattr(a, "custom_dataset_name", "celeba")
+        p0 = os.path.join(tdir, f"{name}_LPIPS_distance_x0_t.tsv")
+        if not os.path.exists(p0) or (ut is None and cosine is None):
+            raise ValueError(f"t_edit / t_addnoise undefined: pass --user_defined_t_edit and --user_defined_t_addnoise, "
+                             f"or --clip_cosine with --lpips_table_dir (looked for {p0}; CLIP is not available offline)")
+        table = _read_tsv(p0)
+        self.t_edit = ut if ut is not None else next(t for t, v in table if v >= LPIPS_th * cosine)
+        if ua is not None:
+            self.t_addnoise = ua
+        else:
+            if getattr(a, "add_noise_from_xt", False):
+                table = _read_tsv(os.path.join(tdir, f"{name}_LPIPS_distance_x.tsv"))
+            self.t_addnoise = next(t for t, v in table if v >= LPIPS_addnoise_th)
+        return cosine
+
+    # ------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def random_noise_pairs(self, model=None, saved_noise=False, save_imgs=False):
+        """[x0, x_rec, x_T] triples with x_T ~ N(0,1) drawn per image on the host (same draw order as :1172-1184)"""
+        c, s = self.config.data.channels, self.config.data.image_size
+        out = {}
+        for mode, n in (("train", self.args.n_train_img), ("test", self.args.n_test_img)):
+            pairs = []
+            for _ in range(n):
+                lat = torch.randn((1, c, s, s))
+                pairs.append([torch.zeros_like(lat), torch.zeros_like(lat), lat])
+            out[mode] = pairs
+        return out
+
+    def _load_latent_pairs(self):
+        """precomputed/<category>_<mode>_t<t_0>_nim<N>_ninv<k>_pairs.pth written by the reference (:974-982,1082)"""
+        a, out = self.args, {}
+        for mode, n in (("train", a.n_train_img), ("test", a.n_test_img)):
+            p = os.path.join('precomputed/', f'{self.config.data.category}_{mode}_t{a.t_0}_nim{n}_ninv{a.n_inv_step}_pairs.pth')
+            if not os.path.exists(p):
+                raise FileNotFoundError(f"{p}: DDIM inversion (precompute_pairs) is not part of this build; use "
+                                        "--load_random_noise or provide the latent cache")
+            out[mode] = torch.load(p, map_location="cpu", weights_only=True)
+        return out
+
+    # ------------------------------------------------------------------------------------------
+    def make_schedule(self, seq, seq_next, hs_coeff, edit=True, addnoise=True):
+        return Schedule(self.betas, seq, seq_next, t_edit=self.t_edit, t_addnoise=self.t_addnoise if addnoise else 0,
+                        hs_coeff=hs_coeff, edit=edit)
+
+    @torch.no_grad()
+    def edit_batch(self, model, x_lat, schedule, noise=None, out=None):
+        """x_T (host or device, [B,3,S,S]) -> edited x_0 on the host.  One graph replay; the H2D copy of x_T and the
+        D2H copy of x_0 are the only transfers.  The N(0,1) draws of the stochastic (eta=1) steps are made on the device
+        up-front, as the reference's torch.randn_like does per step (utils/diffusion_utils.py:97), unless `noise`
+        ([n_stochastic, B, 3, S, S]) is given."""
+        eng = model.engine
+        dev = eng.device
+        if schedule.n_stochastic and noise is None:
+            noise = torch.randn((schedule.n_stochastic, *x_lat.shape), device=dev)
+        elif noise is not None:
+            noise = noise.to(dev, non_blocking=True)
+        x0 = eng.sample(x_lat.to(dev, non_blocking=True), schedule, noise=noise)
+        if out is not None:
+            out.copy_(x0, non_blocking=True)
+            return out
+        return x0.cpu()
+
+    @torch.no_grad()
+    def save_image(self, model, x_lat_tensor, seq_inv, seq_inv_next, save_x0=False, save_x_origin=False,
+                   x0_tensor=None, folder_dir="", file_name="", hs_coeff=(1.0, 1.0), **_unused):
+        """rows of the grid: [x0] [origin DDIM] one row per hs_coeff tuple  (diffusion_latent.py:462-541)"""
+        import torchvision.utils as tvu
+        time_s = time.time()
+        x_list = []
+        if save_x0 and x0_tensor is not None:
+            x_list.append(x0_tensor.cpu())
+        if save_x_origin:
+            sch = self.make_schedule(seq_inv, seq_inv_next, (1.0,), edit=False,
+                                     addnoise=bool(getattr(self.args, "origin_process_addnoise", False)))
+            x_list.append(self.edit_batch(model, x_lat_tensor, sch))
+        if not getattr(self.args, "pass_editing", False):
+            coeffs = hs_coeff if isinstance(hs_coeff, list) else [hs_coeff]
+            for tup in coeffs:
+                x_list.append(self.edit_batch(model, x_lat_tensor, self.make_schedule(seq_inv, seq_inv_next, tup)))
+        x = (torch.cat(x_list, dim=0) + 1) * 0.5
+        grid = tvu.make_grid(x, nrow=self.args.bs_train, padding=1)
+        os.makedirs(folder_dir, exist_ok=True)
+        path = os.path.join(folder_dir, f'{file_name}_ngen{self.args.n_train_step}.png')
+        tvu.save_image(grid, path)
+        print(f'{time.time() - time_s} seconds, {file_name}_ngen{self.args.n_train_step}.png is saved')
+        return x_list
+
+    # ------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def run_test(self):
+        a = self.args
+        print("Running Test")
+        self.set_t_edit_t_addnoise(LPIPS_th=a.lpips_edit_th, LPIPS_addnoise_th=a.lpips_addnoise_th)
+        # ----------- sequences (:560-574)
+        seq_test = [int(s + 1e-6) for s in list(np.linspace(0, 1, a.n_test_step) * a.t_0)]
+        seq_test_next = [-1] + list(seq_test[:-1])
+        # ----------- model
+        model = self.load_pretrained_model()
+        if a.train_delta_block:
+            model.setattr_layers(a.get_h_num)
+        if getattr(a, "train_delta_h", False):
+            raise NotImplementedError("raw delta_h checkpoints (--train_delta_h) use the explicit-Δh branch, which is "
+                                      "not built yet; DeltaBlock checkpoints (--train_delta_block) are")
+        # ----------- Δh checkpoint name resolution (:594-614)
+        exp_id = os.path.split(a.exp)[-1]
+        if a.load_from_checkpoint:
+            save_name = (f'checkpoint/{a.load_from_checkpoint}_LC_{self.config.data.category}_t{a.t_0}_ninv'
+                         f'{a.n_inv_step}_ngen{a.n_train_step}_{a.n_iter - 1}.pth')
+        else:
+            save_name = f'checkpoint/{exp_id}_{a.n_iter - 1}.pth'
+        if a.manual_checkpoint_name:
+            save_name = os.path.join(getattr(a, "checkpoint_dir", "checkpoint"), a.manual_checkpoint_name)
+        elif a.choose_checkpoint_num:
+            save_name = save_name[:-4] + f'_{a.choose_checkpoint_num}.pth'
+        scaling_factor = a.n_train_step / a.n_test_step * a.hs_coeff_delta_h  # :626
+        if a.multiple_attr:
+            attrs = a.multiple_attr.split(' ')
+            coeffs = [float(c) for c in a.multiple_hs_coeff.split(' ')] if a.multiple_hs_coeff else []
+            coeffs = coeffs + [1.0] * (len(attrs) - len(coeffs))
+            save_name_list = [save_name.replace('attribute', attr) for attr in attrs]
+            hs_coeff = tuple([1.0 * a.hs_coeff_origin_h] +
+                             [1.0 / (len(attrs)) ** 0.5 * scaling_factor * c for c in coeffs])  # :654
+        else:
+            save_name_list = [save_name]
+            hs_coeff = (1.0 * a.hs_coeff_origin_h, 1.0 * scaling_factor)  # :659
+        if a.train_delta_block:
+            if not os.path.exists(save_name_list[0]):
+                raise FileNotFoundError(f"checkpoint({save_name_list[0]}) does not exist!")
+            for i in range(a.get_h_num):
+                ck = torch.load(save_name_list[i], map_location="cpu", weights_only=True)
+                getattr(model, f"layer_{i}").load_state_dict(ck["0"])  # :674-676
+        if a.delta_interpolation:  # :726-755
+            vals = np.linspace(a.min_delta, a.max_delta, a.num_delta).tolist()
+            if a.multiple_attr:
+                assert a.get_h_num == 2
+                hs_coeff = [(1.0, v1 * hs_coeff[1], v2 * hs_coeff[2]) for v1 in vals for v2 in vals]
+            else:
+                hs_coeff = [tuple([1.0] + [v * e for e in hs_coeff[1:]]) for v in vals]
+        model = model.to(self.device)
+        if self.world > 1 and torch.distributed.is_initialized():
+            broadcast_weights(model)
+        # ----------- x_T
+        pairs = self.random_noise_pairs(model) if a.load_random_noise else self._load_latent_pairs()
+        results = {}
+        for mode, do, n_img in (("train", a.do_train, a.n_train_img), ("test", a.do_test, a.n_test_img)):
+            if not do:
+                continue
+            x_lat_tensor, x0_tensor, batch_idx = None, None, 0
+            for step, (x0, _, x_lat) in enumerate(pairs[mode]):
+                if a.start_image_id > step:
+                    continue
+                x_lat_tensor = x_lat if x_lat_tensor is None else torch.cat((x_lat_tensor, x_lat), dim=0)
+                if a.use_x0_tensor:
+                    x0_tensor = x0 if x0_tensor is None else torch.cat((x0_tensor, x0), dim=0)
+                if (step + 1) % a.bs_train != 0:
+                    continue
+                if batch_idx % self.world == self.rank:  # batch-sharded across ranks, no per-step communication
+                    results[(mode, step)] = self.save_image(
+                        model, x_lat_tensor, seq_test, seq_test_next, save_x0=a.save_x0,
+                        save_x_origin=a.save_x_origin, x0_tensor=x0_tensor, folder_dir=a.test_image_folder,
+                        file_name=f'{mode}_{step}_{a.n_iter - 1}', hs_coeff=hs_coeff)
+                batch_idx += 1
+                x_lat_tensor, x0_tensor = None, None
+                if step == n_img - 1:
+                    break
+        return results
+
+
+def broadcast_weights(model, src=0):
+    """the one collective of the path: rank `src`'s parameters to every rank (NCCL over NVLink), as one flat buffer"""
+    import torch.distributed as dist
+    params = [p for p in model.parameters()]
+    flat = torch.cat([p.detach().reshape(-1) for p in params])
+    dist.broadcast(flat, src=src)
+    off = 0
+    for p in params:
+        n = p.numel()
+        p.data.copy_(flat[off:off + n].view_as(p))
+        off += n
+    model.refresh_weights()
+
+
+def _read_tsv(path):
+    rows = []
+    with open(path) as f:
+        for line in f:
+            parts = line.strip().split("\t")
+            if len(parts) >= 2:
+                try:
+                    rows.append((int(float(parts[0])), float(parts[1])))
+                except ValueError:
+                    continue
+    return sorted(rows)

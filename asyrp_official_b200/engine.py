@@ -41,6 +41,16 @@ class Act:
         return self.t.shape[2]
 
 
+class Launch:
+    __slots__ = ("fn", "kind", "flops", "nbytes")
+
+    def __init__(self, fn, kind, flops, nbytes):
+        self.fn, self.kind, self.flops, self.nbytes = fn, kind, flops, nbytes
+
+    def __call__(self):
+        self.fn()
+
+
 class Pool:
     """Exact-size free lists of device buffers.  The plan is a fixed launch sequence on one stream, so a buffer
     released after the last op that reads it can be handed to any later op."""
@@ -189,8 +199,9 @@ class Plan:
         self._build()
 
     # ------------------------------------------------------------------ builder primitives
-    def _emit(self, fn):
-        self._cur.append(fn)
+    def _emit(self, fn, kind="misc", flops=0.0, nbytes=0.0):
+        """append one kernel launch; kind / algorithmic flops / algorithmic HBM bytes feed bench.py's roofline"""
+        self._cur.append(Launch(fn, kind, flops, nbytes))
 
     def _act(self, H, W, C, stats=True):
         t = self.pool.alloc((self.N, H, W, C), torch.float16)
@@ -212,7 +223,8 @@ class Plan:
         HW = a.H * a.W
         eps = self.eng.arch.gn_eps
         self._emit(lambda: ops.gn_finalize(a.stats, a.C, b.stats if b else None, b.C if b else 0, gamma, beta, eps, N,
-                                           HW, aff, scale_shift, ss_stride))
+                                           HW, aff, scale_shift, ss_stride), "gn_finalize",
+                   nbytes=4.0 * (a.stats.numel() + (b.stats.numel() if b else 0) + aff.numel()))
         return aff
 
     def _apply(self, srcs, affine, act, resample=RESAMPLE_NONE):
@@ -221,11 +233,13 @@ class Plan:
         H = a.H // 2 if resample == RESAMPLE_AVGPOOL2 else (a.H * 2 if resample == RESAMPLE_UP2 else a.H)
         Wd = a.W // 2 if resample == RESAMPLE_AVGPOOL2 else (a.W * 2 if resample == RESAMPLE_UP2 else a.W)
         out = self._act(H, Wd, C, stats=False)
-        self._emit(lambda: ops.apply(a.t, b.t if b else None, affine, out.t, act, resample))
+        n_in = out.t.numel() * (4 if resample == RESAMPLE_AVGPOOL2 else (0.25 if resample == RESAMPLE_UP2 else 1))
+        self._emit(lambda: ops.apply(a.t, b.t if b else None, affine, out.t, act, resample), "apply",
+                   nbytes=2.0 * (n_in + out.t.numel()))
         return out
 
     def _conv(self, segs, weight, Cout, H, W, ebias=None, ebias_stride=0, residual=None, res_scale=1.0,
-              acc_scale=1.0, stats=True, planar=None):
+              acc_scale=1.0, stats=True, planar=None, algo_flops=None):
         out = None
         if planar is None:
             out = self._act(H, W, Cout, stats=stats)
@@ -233,7 +247,11 @@ class Plan:
                         ebias_stride=ebias_stride, residual=residual.t if residual is not None else None,
                         res_scale=res_scale, acc_scale=acc_scale, stats=out.stats if out else None,
                         out_planar=planar, out_shape=(self.N, H, W, Cout))
-        self._emit(op.launch)
+        ktot = weight.shape[-1]
+        flops = algo_flops if algo_flops is not None else 2.0 * self.N * H * W * Cout * ktot
+        nbytes = 2.0 * (sum(s.t.numel() for s, _ in segs) + weight.numel() + self.N * H * W * Cout
+                        + (residual.t.numel() if residual is not None else 0))
+        self._emit(op.launch, "conv", flops, nbytes)
         return out, op
 
     # ------------------------------------------------------------------ blocks
@@ -287,7 +305,8 @@ class Plan:
         att = self._act(x.H, x.W, C, stats=False)
         N, T = self.N, x.H * x.W
         scale = float(d) ** -0.5  # C^-0.5 (ddpm/diffusion.py:213) == (d^-1/4)^2 (improved_ddpm/unet.py:389-392)
-        self._emit(lambda: ops.attention(qkv.t.view(N, T, 3 * C), att.t.view(N, T, C), heads, d, scale))
+        self._emit(lambda: ops.attention(qkv.t.view(N, T, 3 * C), att.t.view(N, T, C), heads, d, scale), "attention",
+                   flops=4.0 * N * T * T * C, nbytes=2.0 * N * T * 4 * C)
         out, _ = self._conv([(att, MODE_1x1)], W[p + ".wproj"], C, x.H, x.W, ebias=W[p + ".bproj"], residual=x)
         self._free(qkv)
         self._free(att)
@@ -333,15 +352,17 @@ class Plan:
         self.emb_all = torch.zeros(N, eng.emb_total, dtype=torch.float32, device=dev)
         variant = 0 if a.family == "ddpm" else 1
         n0, n1 = a.temb_names
-        self._emit(lambda: ops.timestep_embedding(self.t, e0, variant))
-        self._emit(lambda: ops.linear(e0, W[n0 + ".weight"], W[n0 + ".bias"], e1, act_out=True))
-        self._emit(lambda: ops.linear(e1, W[n1 + ".weight"], W[n1 + ".bias"], self.temb))
-        self._emit(lambda: ops.linear(self.temb, W["emb_cat.w"], W["emb_cat.b"], self.emb_all, act_in=True))
+        self._emit(lambda: ops.timestep_embedding(self.t, e0, variant), "temb")
+        self._emit(lambda: ops.linear(e0, W[n0 + ".weight"], W[n0 + ".bias"], e1, act_out=True), "temb")
+        self._emit(lambda: ops.linear(e1, W[n1 + ".weight"], W[n1 + ".bias"], self.temb), "temb")
+        self._emit(lambda: ops.linear(self.temb, W["emb_cat.w"], W["emb_cat.b"], self.emb_all, act_in=True), "temb",
+                   nbytes=4.0 * W["emb_cat.w"].numel())
         # ---- encoder
         xin = self._act(S, S, 64, stats=False)
-        self._emit(lambda: ops.pack_input(self.x, xin.t))
+        self._emit(lambda: ops.pack_input(self.x, xin.t), "pack_input", nbytes=4.0 * self.x.numel() + 2.0 * xin.t.numel())
         first_ch = a.enc[1][0].cin
-        h, _ = self._conv([(xin, MODE_3x3)], W["conv_in.w"], first_ch, S, S, ebias=W["conv_in.b"])
+        h, _ = self._conv([(xin, MODE_3x3)], W["conv_in.w"], first_ch, S, S, ebias=W["conv_in.b"],
+                          algo_flops=2.0 * N * S * S * first_ch * 9 * a.in_ch)
         self._free(xin)
         hs = [h]
         for stage in a.enc[1:]:
@@ -381,7 +402,8 @@ class Plan:
         self._cur.pop()
         op_nt = ops.ConvOp([(src.t, MODE_1x1)], W[p + ".w1"], out=d1.t, ebias=W[p + ".b1"], stats=d1.stats)
         st = self.eng.state
-        self._emit(lambda: (op_nt if st["ignore_timestep"] else op_t).launch())
+        self._emit(lambda: (op_nt if st["ignore_timestep"] else op_t).launch(), "conv",
+                   2.0 * self.N * h.H * h.W * C * C)
         if src is not h:
             self._free(src)
         aff = self._gn([d1], W[p + ".g2"], W[p + ".be2"])
@@ -411,13 +433,36 @@ class Plan:
         self.pool.release(aff)
         self._free(h)
         self._conv([(an, MODE_3x3)], W["conv_out.w"], 64, an.H, an.W, ebias=W["conv_out.b"], stats=False,
-                   planar=out_planar)
+                   planar=out_planar, algo_flops=2.0 * self.N * an.H * an.W * a.out_ch * 9 * an.C)
         self._free(an)
 
     # ------------------------------------------------------------------ execution
     def set_coeffs(self, hs_coeff):
         for op, i in self.scale_ops:
             op.set_scales(float(hs_coeff[i + 1]), float(hs_coeff[0]) if i == 0 else 1.0)
+
+    def launches(self, edit):
+        """kernel launches of one UNet evaluation"""
+        ops_ = self.enc_ops + (self.delta_ops + self.dec_mod_ops if edit else []) + self.dec_ops
+        return ops_
+
+    def profile(self, edit=True, reps=3):
+        """CUDA-event time of every launch of one UNet evaluation (eager, serialised): list of
+        (kind, ms, algorithmic flops, algorithmic bytes).  Used by bench.py for the per-kernel roofline."""
+        seq = self.launches(edit)
+        best = [float("inf")] * len(seq)
+        for _ in range(reps):
+            evs = []
+            for L in seq:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                L()
+                e1.record()
+                evs.append((e0, e1))
+            torch.cuda.synchronize()
+            for i, (e0, e1) in enumerate(evs):
+                best[i] = min(best[i], e0.elapsed_time(e1))
+        return [(L.kind, ms, L.flops, L.nbytes) for L, ms in zip(seq, best)]
 
     def run_encoder(self):
         for f in self.enc_ops:
@@ -523,7 +568,8 @@ class UNetEngine:
                             zi += 1
                         ops.ddim_update(P.x, P.et, P.et_mod if edit else P.et, z, P.x, None, s.at, s.an, s.c1, s.c2)
 
-                g = {"zbuf": zbuf, "t_table": t_table, "body": body, "graph": None}
+                n_launch = sum(len(P.launches(s.edit and self.n_delta > 0)) + 1 for s in steps)
+                g = {"zbuf": zbuf, "t_table": t_table, "body": body, "graph": None, "launches": n_launch}
                 if use_graph:
                     P.x.copy_(x_T)
                     s_ = torch.cuda.Stream(device=self.device)
@@ -541,9 +587,10 @@ class UNetEngine:
                         body()
                     g["graph"] = cg
                 self.graphs[key] = g
-            P.x.copy_(x_T)
+            self.last_launches = g["launches"]
+            P.x.copy_(x_T, non_blocking=True)
             if n_sto:
-                g["zbuf"].copy_(noise)
+                g["zbuf"].copy_(noise, non_blocking=True)
             if g["graph"] is not None:
                 g["graph"].replay()
             else:

@@ -1,0 +1,125 @@
+/* libasyrp_b200.so — C ABI of the B200-native Asyrp sampling engine (sm_100a).
+ *
+ * The reference (kwonminki/Asyrp_official) has no FFI: its seam for this path is Python call signatures
+ * (utils/diffusion_utils.py:24 denoising_step, models/ddpm/diffusion.py:473 DDPM.forward,
+ * models/improved_ddpm/unet.py:676 UNetModel.forward).  This header is the boundary a maintainer binds instead
+ * of torch's cuDNN/cuBLAS calls; every entry point names the reference operations it replaces.  INTEGRATION.md
+ * shows the ctypes stub (asyrp_official_b200/_lib.py is the shipped one).
+ *
+ * Conventions
+ *  - plain pointers and sizes; all pointers are DEVICE pointers unless noted; the caller owns every buffer
+ *  - activations: NHWC fp16 ("half"); weights: fp16 [Cout][K] with K = taps*Cin, tap-major / channel-minor;
+ *    statistics, affine tables, embeddings, sampler state: fp32
+ *  - `stream` is a cudaStream_t; calls only enqueue work, never synchronise, never allocate device memory
+ *  - return 0 on success, <0 on error (ASYRP_ERR_*); asyrp_last_error() gives the message (thread local)
+ */
+#ifndef ASYRP_B200_H
+#define ASYRP_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ASYRP_OK 0
+#define ASYRP_ERR_INVALID (-1)   /* bad argument / unsupported shape */
+#define ASYRP_ERR_CUDA (-2)      /* CUDA runtime or driver error */
+#define ASYRP_ERR_NO_DEVICE (-3) /* no usable device / driver */
+
+const char* asyrp_last_error(void);
+
+/* ---- implicit-GEMM convolution on tcgen05 tensor cores ------------------------------------------------
+ * Replaces torch.nn.Conv2d / Conv1d(k=1) / bmm call sites of the UNets:
+ *   ResnetBlock.conv1/conv2/nin_shortcut  models/ddpm/diffusion.py:122-149     (3x3 s1 p1, 1x1)
+ *   Downsample.conv (pad (0,1,0,1), s2)   models/ddpm/diffusion.py:96-108
+ *   Upsample.conv                         models/ddpm/diffusion.py:77-88
+ *   AttnBlock.q/k/v/proj_out              models/ddpm/diffusion.py:179-198
+ *   ResBlock in_layers[2]/out_layers[3]/skip_connection, AttentionBlock.qkv/proj_out, DeltaBlock 1x1 convs
+ *                                         models/improved_ddpm/unet.py:224-264,333-336,821-834
+ *   conv_in / conv_out                    models/ddpm/diffusion.py:357-361,424-428 ; unet.py:522-524,654-658
+ * A descriptor lists up to 3 K-segments (sources): a channel concatenation (torch.cat of decoder input and skip,
+ * ddpm/diffusion.py:549) is two segments; a fused 1x1 shortcut is one more segment of the same accumulator.
+ * Epilogue: out = acc_scale*(acc + ebias[n]) + res_scale*residual, stored fp16 NHWC (or fp32 planar channels),
+ * plus per-(sample, tile, channel-pair) partial sums for the GroupNorm that consumes the output. */
+#define ASYRP_CONV_1x1 0
+#define ASYRP_CONV_3x3 1    /* stride 1, zero pad 1 */
+#define ASYRP_CONV_3x3_S2 2 /* stride 2, zero pad right/bottom by 1; source is [N][2H][2W][C] */
+
+typedef struct AsyrpConvSeg {
+  const void* src; /* fp16 NHWC source */
+  int C;           /* channels, multiple of 64 */
+  int mode;        /* ASYRP_CONV_* */
+} AsyrpConvSeg;
+
+typedef struct AsyrpConvDesc {
+  int N, H, W, Cout;     /* output geometry; Cout multiple of 64 */
+  int nseg;              /* 1..3 */
+  AsyrpConvSeg seg[3];
+  const void* weight;    /* fp16 [Cout][K] ([N][Cout][K] if weight_batched), K = sum_seg taps*C */
+  int weight_batched;    /* per-sample weight matrix (batched GEMM, e.g. q k^T) */
+  const float* ebias;    /* fp32 bias row(s): row n at ebias + n*ebias_stride; NULL = none */
+  int ebias_stride;      /* 0: one row shared by all samples (plain bias);
+                            >0: per-sample rows (conv bias + timestep-embedding projection) */
+  const void* residual;  /* fp16 NHWC [N][H][W][Cout] or NULL */
+  float res_scale, acc_scale;
+  void* out;             /* fp16 NHWC [N][H][W][Cout] (ignored when out_planar != NULL) */
+  float* stats;          /* [N][asyrp_conv_stats_tiles(H,W)][Cout/2][2] fp32 (sum, sum of squares) or NULL */
+  float* out_planar;     /* optional fp32 NCHW [N][planar_c][H][W]: output channels [0, planar_c<=8) only */
+  int planar_c;
+} AsyrpConvDesc;
+
+int asyrp_conv_stats_tiles(int H, int W);
+int asyrp_conv_create(const AsyrpConvDesc* desc, void** op); /* encodes TMA descriptors; host only */
+int asyrp_conv_launch(void* op, void* stream);
+int asyrp_conv_set_scales(void* op, float acc_scale, float res_scale); /* hs_coeff of forward(), diffusion.py:512-516 */
+void asyrp_conv_destroy(void* op);
+
+/* ---- GroupNorm(32) statistics -> per-(sample, channel) affine ------------------------------------------
+ * Replaces torch.nn.GroupNorm in Normalize (ddpm/diffusion.py:68-69, eps 1e-6) and GroupNorm32
+ * (improved_ddpm/nn.py:17-19, eps 1e-5).  The normalised tensor may be the concatenation of two conv outputs
+ * (Ca + Cb channels).  scale_shift (optional, [N][>=2C], row stride ss_stride): out = GN(x)*(1+scale)+shift
+ * (improved_ddpm/unet.py:290-294).  affine: [N][C][2] with y = a*x + b. */
+int asyrp_gn_finalize(const float* stats_a, int Ca, int tiles_a, const float* stats_b, int Cb, int tiles_b,
+                      const float* gamma, const float* beta, float eps, int N, int HW, const float* scale_shift,
+                      int ss_stride, float* affine, void* stream);
+
+/* ---- out = resample(act(a*x + b)) over the channel concat of up to two NHWC fp16 sources ------------------
+ * act: 0 identity, 1 SiLU (x*sigmoid(x), ddpm/diffusion.py:63-65).  resample: 0 none, 1 2x2 average pool
+ * (improved_ddpm/unet.py:173-181), 2 nearest x2 (F.interpolate, ddpm/diffusion.py:83-84).  affine NULL = identity. */
+int asyrp_apply(const void* src_a, int Ca, const void* src_b, int Cb, const float* affine, void* out, int N, int Hi,
+                int Wi, int act, int resample, void* stream);
+
+/* x_t fp32 NCHW [N][Cin<=64][H][W] -> fp16 NHWC [N][H][W][64] (zero padded channels): operand of conv_in */
+int asyrp_pack_input(const float* x, void* out, int N, int Cin, int H, int W, void* stream);
+
+/* sinusoidal timestep embedding, [N] -> [N][dim].  variant 0: get_timestep_embedding (ddpm/diffusion.py:42-60);
+ * variant 1: timestep_embedding (improved_ddpm/nn.py:103-121) */
+int asyrp_timestep_embedding(const float* t, float* out, int N, int dim, int variant, void* stream);
+
+/* out[n][o] = bias[o] + sum_i W[o][i]*f(in[n][i]); f = SiLU if act_in; SiLU on the result if act_out.
+ * Replaces temb.dense / temb_proj (ddpm/diffusion.py:349-354,157) and time_embed / emb_layers (unet.py:513-517,239-245) */
+int asyrp_linear(const float* in, int in_stride, const float* W, const float* bias, float* out, int out_stride,
+                 int N, int I, int O, int act_in, int act_out, void* stream);
+
+/* DDIM update (utils/diffusion_utils.py:84-97), fp32, same operation order:
+ *   x0 = (x - em*sqrt(1-at))/sqrt(at);  x_next = sqrt(an)*x0 + c2*et (+ c1*z)
+ * et/em: fp32 planar [N][Ce][HW], channels [0,Cx) are epsilon (learn_sigma split, :47-51); z, x0_out may be NULL;
+ * x_next may alias x. */
+int asyrp_ddim_update(const float* x, const float* et, const float* em, const float* z, float* x_next,
+                      float* x0_out, int N, int Cx, int Ce, int HW, float at, float an, float c1, float c2,
+                      void* stream);
+
+/* out = alpha*a + beta*b, fp16 tensors of `numel` elements (multiple of 8) */
+int asyrp_axpby(const void* a, const void* b, void* out, float alpha, float beta, long long numel, void* stream);
+
+/* NHWC fp16 [N][HW][C] -> NCHW fp32 (API-visible delta_h / middle_h) */
+int asyrp_unpack_nchw(const void* in, float* out, int N, int C, int HW, void* stream);
+
+/* softmax(q k^T * scale) v per (sample, head).  qkv: fp16 [N][T][3*heads*head_dim] laid out [q | k | v], head h at
+ * h*head_dim; out fp16 [N][T][heads*head_dim].  Replaces the bmm/softmax/bmm of AttnBlock.forward
+ * (ddpm/diffusion.py:206-221) and QKVAttentionLegacy.forward (improved_ddpm/unet.py:379-396). */
+int asyrp_attention(const void* qkv, void* out, int N, int T, int heads, int head_dim, float scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ASYRP_B200_H */
