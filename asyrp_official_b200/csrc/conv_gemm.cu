@@ -42,7 +42,8 @@ struct ConvParams {
   ConvSegDev seg[kMaxSeg];
   int nseg;
   int N, H, W, Cout;      // output geometry
-  int TW, TH, NB;         // pixel tile: TW x TH pixels of NB samples, TW*TH*NB == 128
+  int TW, TH, NB;         // pixel sub-tile: TW x TH pixels of NB samples, TW*TH*NB == 128
+  int MT;                 // sub-tiles (stacked in y) per CTA tile: 1 or 2; all share every weight tile
   int tiles_x, tiles_y, tiles_n, m_tiles, n_tiles;
   int a_stages, b_stages;
   uint32_t a_stage_bytes;  // ring slot size for A copies
@@ -58,7 +59,7 @@ struct ConvParams {
   int b_batched;           // weights have a per-sample batch dimension (attention GEMMs)
 };
 
-template <int BN>
+template <int BN, int MT>
 __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B operands need 1024B alignment
@@ -67,7 +68,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   constexpr uint32_t kBStage = BN * 128;
-  constexpr uint32_t kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
+  constexpr uint32_t kTmemCols = 2 * MT * BN;  // two accumulator sets (epilogue / MMA overlap)
+  static_assert(kTmemCols <= 512 && kTmemCols >= 32, "TMEM budget");
 
   uint8_t* sA = smem;
   uint8_t* sB = sA + p.a_stages * p.a_stage_bytes;
@@ -80,6 +82,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
   float* s_stats = reinterpret_cast<float*>(tmem_slot + 4);  // [2][4][BN/32][32]
+  const int THT = MT * p.TH;  // rows of the CTA tile
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.a_stages; ++i) {
@@ -119,13 +122,13 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int mt = tile % p.m_tiles, nt = tile / p.m_tiles;
         const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, tn = mt / (p.tiles_x * p.tiles_y);
-        const int x0 = tx * p.TW, y0 = ty * p.TH, n0 = tn * p.NB;
+        const int x0 = tx * p.TW, y0 = ty * THT, n0 = tn * p.NB;
         const int bz = p.b_batched ? n0 : 0;
         for (int s = 0; s < p.nseg; ++s) {
           const ConvSegDev sg = p.seg[s];
           const int ncopies = sg.mode == 0 ? 1 : (sg.mode == 1 ? 3 : 9);
           const int ntaps = sg.mode == 1 ? 3 : 1;
-          const uint32_t a_bytes = (sg.mode == 1 ? (p.TH + 2) : p.TH) * p.row_bytes;
+          const uint32_t a_bytes = (sg.mode == 1 ? (THT + 2) : THT) * p.row_bytes;
           for (int ch = 0; ch < sg.nchunks; ++ch) {
             for (int cp = 0; cp < ncopies; ++cp) {
               mbar_wait(&emptyA[sa], pa ^ 1);
@@ -166,7 +169,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
+        const uint32_t d_tmem = tmem_base + acc * (MT * BN);
         uint32_t accumulate = 0;
         for (int s = 0; s < p.nseg; ++s) {
           const ConvSegDev sg = p.seg[s];
@@ -180,14 +183,17 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
               for (int tp = 0; tp < ntaps; ++tp) {
                 mbar_wait(&fullB[sb], pb);
                 tc_fence_after();
-                const uint32_t a_addr = a_base + tp * p.row_bytes;  // dy tap = row shift (mode 1)
                 const uint32_t b_addr = smem_u32(sB + sb * kBStage);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  umma_f16(d_tmem, umma_desc_k128(a_addr + k * 32), umma_desc_k128(b_addr + k * 32), idesc,
-                           accumulate);
-                  accumulate = 1;
+                for (int sub = 0; sub < MT; ++sub) {
+                  // dy tap = row shift (mode 1); sub-tile = TH rows further down the same copy
+                  const uint32_t a_addr = a_base + (sub * p.TH + tp) * p.row_bytes;
+#pragma unroll
+                  for (int k = 0; k < 4; ++k)
+                    umma_f16(d_tmem + sub * BN, umma_desc_k128(a_addr + k * 32), umma_desc_k128(b_addr + k * 32),
+                             idesc, (accumulate | k) ? 1u : 0u);
                 }
+                accumulate = 1;
                 umma_commit(&emptyB[sb]);
                 if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
               }
@@ -213,17 +219,23 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
       const uint32_t acc_phase = (it >> 1) & 1;
       const int mt = tile % p.m_tiles, nt = tile / p.m_tiles;
       const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, tn = mt / tiles_per_sample;
-      const int x = tx * p.TW + xx, y = ty * p.TH + yy, n = tn * p.NB + nn;
-      const bool valid = (x < p.W) && (y < p.H) && (n < p.N);
-      const size_t pix = (static_cast<size_t>(n) * p.H + y) * p.W + x;
+      const int x = tx * p.TW + xx, n = tn * p.NB + nn;
       float* st = s_stats + acc * (4 * BN);
+      float sacc[BN / 32];
+#pragma unroll
+      for (int i = 0; i < BN / 32; ++i) sacc[i] = 0.f;
 
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
 #pragma unroll 1
+      for (int sub = 0; sub < MT; ++sub) {
+      const int y = ty * THT + sub * p.TH + yy;
+      const bool valid = (x < p.W) && (y < p.H) && (n < p.N);
+      const size_t pix = (static_cast<size_t>(n) * p.H + y) * p.W + x;
+#pragma unroll
       for (int cc = 0; cc < BN / 32; ++cc) {
         uint32_t r[32];
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + cc * 32, r);
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * (MT * BN) + sub * BN + cc * 32, r);
         tmem_ld_wait();
         const int c0 = nt * BN + cc * 32;
         float v[32];
@@ -299,7 +311,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
             }
             // s_stats[acc][sn?]: NB>1 tiles are tiny layers; fold sn into the slot by direct global write
             if (p.NB == 1) {
-              st[(q * (BN / 32) + cc) * 32 + lane] = w[0];
+              sacc[cc] += w[0];
             } else {
               // one atomic per (warp, sample, slot): few tiles, low contention, fp32 order-dependent only
               // across the 4 warps of a tile -> made deterministic by writing per-warp slots
@@ -313,6 +325,11 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
             }
           }
         }
+      }
+      }  // sub
+      if (p.stats != nullptr && p.NB == 1) {
+#pragma unroll
+        for (int cc = 0; cc < BN / 32; ++cc) st[(q * (BN / 32) + cc) * 32 + lane] = sacc[cc];
       }
       // accumulator fully drained into registers/global: release it to the MMA warp
       tc_fence_before();
@@ -349,6 +366,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
 struct ConvOp {
   ConvParams p;
   int BN;
+  int MT;
   int grid;
   size_t smem_bytes;
 };
@@ -356,6 +374,14 @@ struct ConvOp {
 }  // namespace asyrp
 
 using namespace asyrp;
+
+static const void* conv_kernel_ptr(int BN, int MT) {
+  if (BN == 256) return reinterpret_cast<const void*>(&conv_gemm_kernel<256, 1>);
+  if (BN == 128) return MT == 2 ? reinterpret_cast<const void*>(&conv_gemm_kernel<128, 2>)
+                                : reinterpret_cast<const void*>(&conv_gemm_kernel<128, 1>);
+  return MT == 2 ? reinterpret_cast<const void*>(&conv_gemm_kernel<64, 2>)
+                 : reinterpret_cast<const void*>(&conv_gemm_kernel<64, 1>);
+}
 
 extern "C" {
 
@@ -381,6 +407,18 @@ struct AsyrpConvDesc {
   int planar_c;
 };
 
+static int conv_bn(int Cout) { return (Cout % 256 == 0) ? 256 : (Cout % 128 == 0 ? 128 : 64); }
+
+static void conv_tile_shape(int H, int W, int* TW, int* TH, int* NB);
+
+// CTA tile = MT sub-tiles of 128 pixels stacked in y.  Two sub-tiles halve the weight (B operand) traffic per
+// FLOP; TMEM holds 2*MT*BN fp32 columns (<= 512), so MT = 2 needs BN <= 128.
+static int conv_mt(int H, int W, int Cout) {
+  int TW, TH, NB;
+  conv_tile_shape(H, W, &TW, &TH, &NB);
+  return (conv_bn(Cout) <= 128 && NB == 1 && H > 1 && H % (2 * TH) == 0) ? 2 : 1;
+}
+
 static void conv_tile_shape(int H, int W, int* TW, int* TH, int* NB) {
   int tw, th;
   if (H == 1) {
@@ -401,10 +439,11 @@ static void conv_tile_shape(int H, int W, int* TW, int* TH, int* NB) {
 
 // number of pixel tiles per sample the stats buffer must hold: stats is [N][tiles][Cout/2][2] floats.
 // For layers whose tile spans several samples (NB>1) the kernel writes one slot per epilogue warp (4).
-ASYRP_API int asyrp_conv_stats_tiles(int H, int W) {
+ASYRP_API int asyrp_conv_stats_tiles(int H, int W, int Cout) {
   int TW, TH, NB;
   conv_tile_shape(H, W, &TW, &TH, &NB);
-  const int tiles = ((W + TW - 1) / TW) * ((H + TH - 1) / TH);
+  const int tht = TH * conv_mt(H, W, Cout);
+  const int tiles = ((W + TW - 1) / TW) * ((H + tht - 1) / tht);
   return NB == 1 ? tiles : tiles * 4;
 }
 
@@ -420,11 +459,13 @@ ASYRP_API int asyrp_conv_create(const AsyrpConvDesc* d, void** out_op) {
   ASYRP_REQUIRE(p.TW * p.TH * p.NB == 128, "asyrp_conv_create: cannot tile H=%d W=%d into 128 pixels", d->H,
                 d->W);
   ASYRP_REQUIRE(!(d->weight_batched && p.NB != 1), "asyrp_conv_create: batched weights need NB==1");
+  op->MT = p.MT = conv_mt(d->H, d->W, d->Cout);
+  const int THT = p.TH * p.MT;
   p.tiles_x = (d->W + p.TW - 1) / p.TW;
-  p.tiles_y = (d->H + p.TH - 1) / p.TH;
+  p.tiles_y = (d->H + THT - 1) / THT;
   p.tiles_n = (d->N + p.NB - 1) / p.NB;
   p.m_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
-  op->BN = (d->Cout % 256 == 0) ? 256 : (d->Cout % 128 == 0 ? 128 : 64);
+  op->BN = conv_bn(d->Cout);
   p.n_tiles = d->Cout / op->BN;
   p.row_bytes = p.NB * p.TW * 128;
   p.nseg = d->nseg;
@@ -447,12 +488,12 @@ ASYRP_API int asyrp_conv_create(const AsyrpConvDesc* d, void** out_op) {
       const uint64_t H = d->H, W = d->W;
       dims[0] = C; dims[1] = W; dims[2] = d->N; dims[3] = 1; dims[4] = H;
       strides[0] = C * 2; strides[1] = H * W * C * 2; strides[2] = W * C * 2; strides[3] = W * C * 2;
-      box[0] = 64; box[1] = p.TW; box[2] = p.NB; box[3] = 1; box[4] = sg.mode == 1 ? p.TH + 2 : p.TH;
+      box[0] = 64; box[1] = p.TW; box[2] = p.NB; box[3] = 1; box[4] = sg.mode == 1 ? THT + 2 : THT;
     } else {
       const uint64_t Hi = 2 * d->H, Wi = 2 * d->W;
       dims[0] = 2 * C; dims[1] = Wi / 2; dims[2] = d->N; dims[3] = 2; dims[4] = Hi / 2;
       strides[0] = 2 * C * 2; strides[1] = Hi * Wi * C * 2; strides[2] = Wi * C * 2; strides[3] = 2 * Wi * C * 2;
-      box[0] = 64; box[1] = p.TW; box[2] = p.NB; box[3] = 1; box[4] = p.TH;
+      box[0] = 64; box[1] = p.TW; box[2] = p.NB; box[3] = 1; box[4] = THT;
     }
     int rc = encode_tensor_map(&p.tmA[s], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, sg.src, dims, strides, box,
                                CU_TENSOR_MAP_SWIZZLE_128B);
@@ -468,10 +509,10 @@ ASYRP_API int asyrp_conv_create(const AsyrpConvDesc* d, void** out_op) {
     if (rc != ASYRP_OK) { delete op; return rc; }
   }
   p.b_batched = d->weight_batched;
-  p.a_stage_bytes = (any3 ? p.TH + 2 : p.TH) * p.row_bytes;
+  p.a_stage_bytes = (any3 ? THT + 2 : THT) * p.row_bytes;
   // shared memory budget: ~205 KB of operand rings
   const uint32_t b_stage = op->BN * 128;
-  p.a_stages = any3 ? 4 : 4;
+  p.a_stages = p.MT == 2 ? 3 : 4;
   p.b_stages = op->BN == 256 ? 4 : 6;
   while (p.a_stages * p.a_stage_bytes + p.b_stages * b_stage > 210 * 1024 && p.a_stages > 2) --p.a_stages;
   while (p.a_stages * p.a_stage_bytes + p.b_stages * b_stage > 210 * 1024 && p.b_stages > 2) --p.b_stages;
@@ -494,13 +535,8 @@ ASYRP_API int asyrp_conv_create(const AsyrpConvDesc* d, void** out_op) {
   if (sms <= 0) { delete op; return ASYRP_ERR_NO_DEVICE; }
   const int total = p.m_tiles * p.n_tiles;
   op->grid = total < sms ? total : sms;
-  cudaError_t e = cudaSuccess;
-  if (op->BN == 256)
-    e = cudaFuncSetAttribute(conv_gemm_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  else if (op->BN == 128)
-    e = cudaFuncSetAttribute(conv_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  else
-    e = cudaFuncSetAttribute(conv_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaError_t e = cudaFuncSetAttribute(conv_kernel_ptr(op->BN, op->MT), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       227 * 1024);
   if (e != cudaSuccess) {
     set_error("asyrp_conv_create: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     delete op;
@@ -514,13 +550,9 @@ ASYRP_API int asyrp_conv_launch(void* handle, void* stream) {
   ASYRP_REQUIRE(handle, "asyrp_conv_launch: null op");
   ConvOp* op = static_cast<ConvOp*>(handle);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (op->BN == 256)
-    conv_gemm_kernel<256><<<op->grid, kNumThreads, op->smem_bytes, st>>>(op->p);
-  else if (op->BN == 128)
-    conv_gemm_kernel<128><<<op->grid, kNumThreads, op->smem_bytes, st>>>(op->p);
-  else
-    conv_gemm_kernel<64><<<op->grid, kNumThreads, op->smem_bytes, st>>>(op->p);
-  ASYRP_CHECK_CUDA(cudaGetLastError());
+  void* args[] = {&op->p};
+  ASYRP_CHECK_CUDA(cudaLaunchKernel(conv_kernel_ptr(op->BN, op->MT), dim3(op->grid), dim3(kNumThreads), args,
+                                    op->smem_bytes, st));
   return ASYRP_OK;
 }
 

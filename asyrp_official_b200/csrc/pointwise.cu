@@ -108,66 +108,80 @@ __device__ __forceinline__ void store8(__half* p, const float (&f)[8]) {
   *reinterpret_cast<uint4*>(p) = u;
 }
 
+// Thread mapping: a thread owns ONE channel octet (its affine coefficients stay in registers) and walks output
+// pixels; consecutive threads cover consecutive octets of a pixel, so a warp reads/writes whole 128B+ lines.
+template <int RESAMPLE>
 __global__ void __launch_bounds__(256) apply_kernel(const ApplyParams p) {
   const int C = p.Ca + p.Cb;
-  const int oct_per_pix = C / 8;
-  const size_t total = static_cast<size_t>(p.N) * p.Ho * p.Wo * oct_per_pix;
-  for (size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
-       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int oc = static_cast<int>(idx % oct_per_pix);
-    size_t pix = idx / oct_per_pix;
-    const int xo = static_cast<int>(pix % p.Wo);
-    pix /= p.Wo;
-    const int yo = static_cast<int>(pix % p.Ho);
-    const int n = static_cast<int>(pix / p.Ho);
-    const int c = oc * 8;
-    const __half* src;
-    int Cs, cs;
-    if (c < p.Ca) { src = p.src_a; Cs = p.Ca; cs = c; }
-    else { src = p.src_b; Cs = p.Cb; cs = c - p.Ca; }
-    float a[8], b[8];
-    if (p.affine != nullptr) {
-      const float4* ap = reinterpret_cast<const float4*>(p.affine + (static_cast<size_t>(n) * C + c) * 2);
+  const int octs = C >> 3;                 // octets per pixel
+  const int lanes = blockDim.x / octs;     // pixels processed concurrently by a block (host guarantees octs | 256)
+  const int oc = threadIdx.x % octs, pl = threadIdx.x / octs;
+  const int n = blockIdx.y;
+  const int c = oc * 8;
+  const __half* src;
+  int Cs, cs;
+  if (c < p.Ca) { src = p.src_a; Cs = p.Ca; cs = c; }
+  else { src = p.src_b; Cs = p.Cb; cs = c - p.Ca; }
+  src += static_cast<size_t>(n) * p.Hi * p.Wi * Cs + cs;
+  __half* dst = p.out + static_cast<size_t>(n) * p.Ho * p.Wo * C + c;
+  float a[8], b[8];
+  if (p.affine != nullptr) {
+    const float4* ap = reinterpret_cast<const float4*>(p.affine + (static_cast<size_t>(n) * C + c) * 2);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float4 t = ap[k];
-        a[2 * k] = t.x; b[2 * k] = t.y; a[2 * k + 1] = t.z; b[2 * k + 1] = t.w;
-      }
-    } else {
-#pragma unroll
-      for (int k = 0; k < 8; ++k) { a[k] = 1.f; b[k] = 0.f; }
+    for (int k = 0; k < 4; ++k) {
+      const float4 t = ap[k];
+      a[2 * k] = t.x; b[2 * k] = t.y; a[2 * k + 1] = t.z; b[2 * k + 1] = t.w;
     }
-    float o[8];
-    if (p.resample == 1) {
+  } else {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) o[k] = 0.f;
+    for (int k = 0; k < 8; ++k) { a[k] = 1.f; b[k] = 0.f; }
+  }
+  const int npix = p.Ho * p.Wo;
+  const int stride = gridDim.x * lanes;
+  constexpr int U = RESAMPLE == 1 ? 1 : 4;  // output pixels in flight per thread
+  for (int base = blockIdx.x * lanes + pl; base < npix; base += stride * U) {
+    float v[U][RESAMPLE == 1 ? 4 : 1][8];
 #pragma unroll
-      for (int dy = 0; dy < 2; ++dy)
+    for (int u = 0; u < U; ++u) {
+      const int pix = base + u * stride;
+      if (pix < npix) {
+        if (RESAMPLE == 0) {
+          load8(src + static_cast<size_t>(pix) * Cs, v[u][0]);
+        } else {
+          const int yo = pix / p.Wo, xo = pix - yo * p.Wo;
+          if (RESAMPLE == 2) {
+            load8(src + (static_cast<size_t>(yo >> 1) * p.Wi + (xo >> 1)) * Cs, v[u][0]);
+          } else {
 #pragma unroll
-        for (int dx = 0; dx < 2; ++dx) {
-          float v[8];
-          load8(src + ((static_cast<size_t>(n) * p.Hi + 2 * yo + dy) * p.Wi + 2 * xo + dx) * Cs + cs, v);
+            for (int q = 0; q < 4; ++q)
+              load8(src + (static_cast<size_t>(2 * yo + (q >> 1)) * p.Wi + 2 * xo + (q & 1)) * Cs,
+                    v[u][RESAMPLE == 1 ? q : 0]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int pix = base + u * stride;
+      if (pix < npix) {
+        float o[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = 0.f;
+#pragma unroll
+        for (int q = 0; q < (RESAMPLE == 1 ? 4 : 1); ++q)
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
-            float t = a[k] * v[k] + b[k];
+            float t = fmaf(a[k], v[u][q][k], b[k]);
             if (p.act) t = silu_f(t);
             o[k] += t;
           }
+        if (RESAMPLE == 1) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) o[k] *= 0.25f;
         }
-#pragma unroll
-      for (int k = 0; k < 8; ++k) o[k] *= 0.25f;
-    } else {
-      const int yi = p.resample == 2 ? (yo >> 1) : yo, xi = p.resample == 2 ? (xo >> 1) : xo;
-      float v[8];
-      load8(src + ((static_cast<size_t>(n) * p.Hi + yi) * p.Wi + xi) * Cs + cs, v);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        float t = a[k] * v[k] + b[k];
-        if (p.act) t = silu_f(t);
-        o[k] = t;
+        store8(dst + static_cast<size_t>(pix) * C, o);
       }
     }
-    store8(p.out + ((static_cast<size_t>(n) * p.Ho + yo) * p.Wo + xo) * C + c, o);
   }
 }
 
@@ -324,8 +338,22 @@ ASYRP_API int asyrp_apply(const void* src_a, int Ca, const void* src_b, int Cb, 
   p.Ho = resample == 1 ? Hi / 2 : (resample == 2 ? Hi * 2 : Hi);
   p.Wo = resample == 1 ? Wi / 2 : (resample == 2 ? Wi * 2 : Wi);
   p.act = act; p.resample = resample;
-  const size_t total = static_cast<size_t>(N) * p.Ho * p.Wo * ((Ca + Cb) / 8);
-  apply_kernel<<<grid_for(total, 256, 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  const int octs = (Ca + Cb) / 8;
+  ASYRP_REQUIRE(octs >= 1 && octs <= 256, "asyrp_apply: unsupported channel count %d (max 2048)", Ca + Cb);
+  // block = lanes * octs threads (<= 256): `lanes` pixels at a time, one channel octet per thread
+  const int lanes = 256 / octs;
+  const int threads = lanes * octs;
+  const int npix = p.Ho * p.Wo;
+  int gx = (npix + lanes * 4 - 1) / (lanes * 4);
+  const int cap = (sm_count() > 0 ? sm_count() : 148) * 8;
+  const int max_gx = cap / N > 0 ? cap / N : 1;
+  if (gx > max_gx) gx = max_gx;
+  if (gx < 1) gx = 1;
+  const dim3 grid(gx, N);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (resample == 0) apply_kernel<0><<<grid, threads, 0, st>>>(p);
+  else if (resample == 1) apply_kernel<1><<<grid, threads, 0, st>>>(p);
+  else apply_kernel<2><<<grid, threads, 0, st>>>(p);
   ASYRP_CHECK_CUDA(cudaGetLastError());
   return ASYRP_OK;
 }

@@ -207,7 +207,7 @@ class Plan:
         t = self.pool.alloc((self.N, H, W, C), torch.float16)
         st = None
         if stats:
-            st = self.pool.alloc((self.N, ops.conv_stats_tiles(H, W), C // 2, 2), torch.float32)
+            st = self.pool.alloc((self.N, ops.conv_stats_tiles(H, W, C), C // 2, 2), torch.float32)
         return Act(t, st)
 
     def _free(self, act):

@@ -39,13 +39,13 @@ def pack_conv_weight(w):
     return w.permute(0, 2, 3, 1).reshape(o, -1).to(torch.float16).contiguous()
 
 
-def conv_stats_tiles(H, W):
-    return _lib.load().asyrp_conv_stats_tiles(H, W)
+def conv_stats_tiles(H, W, C):
+    return _lib.load().asyrp_conv_stats_tiles(H, W, C)
 
 
 def new_stats(N, H, W, C, device):
     """Partial GroupNorm sums written by a conv epilogue: [N][tiles][C/2][2] fp32."""
-    return torch.zeros(N, conv_stats_tiles(H, W), C // 2, 2, dtype=torch.float32, device=device)
+    return torch.zeros(N, conv_stats_tiles(H, W, C), C // 2, 2, dtype=torch.float32, device=device)
 
 
 class ConvOp:

@@ -104,7 +104,6 @@ def cpu_leg(family, key, traj_steps, n_edit, iters=1):
     non-edit step (t=300, index=0 -> the reference still runs both decoders), scaled to the full trajectory"""
     from oracle import adm as oa, ddpm as od, sampler as osmp  # checker / baseline only
     from asyrp_official_b200 import synthetic
-    torch.set_num_threads(os.cpu_count())
     m = build_model(family, key, "cpu")
     sd = {k: v.float() for k, v in m.state_dict().items()}
     if family == "ddpm":
@@ -117,8 +116,12 @@ def cpu_leg(family, key, traj_steps, n_edit, iters=1):
     g = torch.Generator().manual_seed(1234)
     x = torch.randn(1, 3, 256, 256, generator=g)
     ls = family == "adm"
-    best_e, best_p = float("inf"), float("inf")
-    for _ in range(iters):
+    best_e, best_p, best_thr = float("inf"), float("inf"), os.cpu_count()
+    # torch's CPU conv does not always scale to every core of a large host: time with all cores and with 32 threads,
+    # report the faster (threads used are stated)
+    for thr in sorted({os.cpu_count(), min(32, os.cpu_count())}):
+      torch.set_num_threads(thr)
+      for _ in range(iters):
         t0 = time.perf_counter()
         osmp.denoising_step(x, torch.ones(1) * 999, torch.ones(1) * 973, model=fwd, b=betas, learn_sigma=ls, index=0,
                             t_edit=500, hs_coeff=(1.0, 1.0))
@@ -126,7 +129,9 @@ def cpu_leg(family, key, traj_steps, n_edit, iters=1):
         osmp.denoising_step(x, torch.ones(1) * 307, torch.ones(1) * 281, model=fwd, b=betas, learn_sigma=ls, index=0,
                             t_edit=500, hs_coeff=(1.0, 1.0))
         t2 = time.perf_counter()
-        best_e, best_p = min(best_e, t1 - t0), min(best_p, t2 - t1)
+        if (t1 - t0) + (t2 - t1) < best_e + best_p:
+            best_e, best_p, best_thr = t1 - t0, t2 - t1, thr
+    torch.set_num_threads(best_thr)
     traj_s = n_edit * best_e + (traj_steps - n_edit) * best_p
     return {"value": 1.0 / traj_s, "unit": "img/s", "cores": torch.get_num_threads(), "kind": "port",
             "sample": f"B=1: 1 edit step ({best_e:.2f}s) + 1 non-edit step ({best_p:.2f}s) of the {traj_steps}-step "

@@ -24,7 +24,8 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     assert lib.asyrp_last_error() is not None
     # pure host helper (no device): tile bookkeeping for the GroupNorm partial sums
-    assert lib.asyrp_conv_stats_tiles(256, 256) == 512 and lib.asyrp_conv_stats_tiles(8, 8) == 4
+    assert lib.asyrp_conv_stats_tiles(256, 256, 256) == 512 and lib.asyrp_conv_stats_tiles(256, 256, 128) == 256
+    assert lib.asyrp_conv_stats_tiles(8, 8, 512) == 4
 
 
 def test_no_cpu_fallback():
