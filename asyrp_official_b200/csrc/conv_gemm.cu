@@ -31,7 +31,8 @@ static constexpr int kNumThreads = 192;
 
 struct ConvSegDev {
   int nchunks;  // C / 64
-  int mode;     // 0: 1x1, 1: 3x3 stride 1, 2: 3x3 stride 2 (parity view)
+  int mode;     // 0: 1x1, 1: 3x3 stride 1 (three dx-shifted copies), 2: 3x3 stride 2 (parity view),
+                // 3: 3x3 stride 1 from ONE halo tile (TW == 8: every tap is an address offset into it)
   int kbase;    // first K column of this segment in the weight matrix
   int C;        // channels of the source
 };
@@ -126,15 +127,18 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
         const int bz = p.b_batched ? n0 : 0;
         for (int s = 0; s < p.nseg; ++s) {
           const ConvSegDev sg = p.seg[s];
-          const int ncopies = sg.mode == 0 ? 1 : (sg.mode == 1 ? 3 : 9);
-          const int ntaps = sg.mode == 1 ? 3 : 1;
-          const uint32_t a_bytes = (sg.mode == 1 ? (THT + 2) : THT) * p.row_bytes;
+          const int ncopies = (sg.mode == 0 || sg.mode == 3) ? 1 : (sg.mode == 1 ? 3 : 9);
+          const int ntaps = sg.mode == 1 ? 3 : (sg.mode == 3 ? 9 : 1);
+          const uint32_t a_bytes = sg.mode == 3 ? (THT + 2) * (p.TW + 2) * 128u
+                                                : (sg.mode == 1 ? (THT + 2) : THT) * p.row_bytes;
           for (int ch = 0; ch < sg.nchunks; ++ch) {
             for (int cp = 0; cp < ncopies; ++cp) {
               mbar_wait(&emptyA[sa], pa ^ 1);
               mbar_arrive_expect_tx(&fullA[sa], a_bytes);
               uint8_t* dst = sA + sa * p.a_stage_bytes;
-              if (sg.mode == 0) {
+              if (sg.mode == 3) {
+                tma_load_5d(dst, &p.tmA[s], &fullA[sa], ch * 64, x0 - 1, n0, 0, y0 - 1);
+              } else if (sg.mode == 0) {
                 tma_load_5d(dst, &p.tmA[s], &fullA[sa], ch * 64, x0, n0, 0, y0);
               } else if (sg.mode == 1) {
                 tma_load_5d(dst, &p.tmA[s], &fullA[sa], ch * 64, x0 + cp - 1, n0, 0, y0 - 1);
@@ -146,7 +150,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
               if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
               for (int tp = 0; tp < ntaps; ++tp) {
                 // tap index in the weight matrix: ky*3+kx
-                const int tap = sg.mode == 0 ? 0 : (sg.mode == 1 ? tp * 3 + cp : cp);
+                const int tap = sg.mode == 0 ? 0 : (sg.mode == 1 ? tp * 3 + cp : (sg.mode == 3 ? tp : cp));
                 mbar_wait(&emptyB[sb], pb ^ 1);
                 mbar_arrive_expect_tx(&fullB[sb], kBStage);
                 tma_load_3d(sB + sb * kBStage, &p.tmB, &fullB[sb], sg.kbase + tap * sg.C + ch * 64, nt * BN, bz);
@@ -173,8 +177,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
         uint32_t accumulate = 0;
         for (int s = 0; s < p.nseg; ++s) {
           const ConvSegDev sg = p.seg[s];
-          const int ncopies = sg.mode == 0 ? 1 : (sg.mode == 1 ? 3 : 9);
-          const int ntaps = sg.mode == 1 ? 3 : 1;
+          const int ncopies = (sg.mode == 0 || sg.mode == 3) ? 1 : (sg.mode == 1 ? 3 : 9);
+          const int ntaps = sg.mode == 1 ? 3 : (sg.mode == 3 ? 9 : 1);
+          // byte strides inside the A stage: between 8-row groups, between sub-tiles, per ky / kx tap step
+          const uint32_t halo_pitch = (p.TW + 2) * 128u;
+          const uint32_t sbo = sg.mode == 3 ? halo_pitch : 1024u;
+          const uint32_t sub_stride = sg.mode == 3 ? p.TH * halo_pitch : p.TH * p.row_bytes;
           for (int ch = 0; ch < sg.nchunks; ++ch) {
             for (int cp = 0; cp < ncopies; ++cp) {
               mbar_wait(&fullA[sa], pa);
@@ -184,13 +192,14 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
                 mbar_wait(&fullB[sb], pb);
                 tc_fence_after();
                 const uint32_t b_addr = smem_u32(sB + sb * kBStage);
+                // mode 1: dy tap = row shift inside the dx copy; mode 3: (ky, kx) = pixel offset inside the halo tile
+                const uint32_t tap_off = sg.mode == 3 ? (tp / 3) * halo_pitch + (tp % 3) * 128u : tp * p.row_bytes;
 #pragma unroll
                 for (int sub = 0; sub < MT; ++sub) {
-                  // dy tap = row shift (mode 1); sub-tile = TH rows further down the same copy
-                  const uint32_t a_addr = a_base + (sub * p.TH + tp) * p.row_bytes;
+                  const uint32_t a_addr = a_base + sub * sub_stride + tap_off;
 #pragma unroll
                   for (int k = 0; k < 4; ++k)
-                    umma_f16(d_tmem + sub * BN, umma_desc_k128(a_addr + k * 32), umma_desc_k128(b_addr + k * 32),
+                    umma_f16(d_tmem + sub * BN, umma_desc_k128(a_addr + k * 32, sbo), umma_desc_k128(b_addr + k * 32),
                              idesc, (accumulate | k) ? 1u : 0u);
                 }
                 accumulate = 1;
@@ -409,18 +418,26 @@ struct AsyrpConvDesc {
 
 static int conv_bn(int Cout) { return (Cout % 256 == 0) ? 256 : (Cout % 128 == 0 ? 128 : 64); }
 
-static void conv_tile_shape(int H, int W, int* TW, int* TH, int* NB);
+static void conv_tile_shape(int H, int W, int halo, int* TW, int* TH, int* NB);
+
+// A 3x3/s1 conv whose output is at least 8 wide and 16 tall uses 8x16-pixel sub-tiles fed from one halo tile per
+// 64-channel chunk ("halo" geometry, segment mode 3); otherwise three dx-shifted copies (mode 1).
+static int conv_halo_ok(int H, int W) { return H % 16 == 0 && W % 8 == 0; }
 
 // CTA tile = MT sub-tiles of 128 pixels stacked in y.  Two sub-tiles halve the weight (B operand) traffic per
 // FLOP; TMEM holds 2*MT*BN fp32 columns (<= 512), so MT = 2 needs BN <= 128.
-static int conv_mt(int H, int W, int Cout) {
+static int conv_mt(int H, int W, int Cout, int halo) {
   int TW, TH, NB;
-  conv_tile_shape(H, W, &TW, &TH, &NB);
+  conv_tile_shape(H, W, halo, &TW, &TH, &NB);
   return (conv_bn(Cout) <= 128 && NB == 1 && H > 1 && H % (2 * TH) == 0) ? 2 : 1;
 }
 
-static void conv_tile_shape(int H, int W, int* TW, int* TH, int* NB) {
+static void conv_tile_shape(int H, int W, int halo, int* TW, int* TH, int* NB) {
   int tw, th;
+  if (halo) {
+    *TW = 8; *TH = 16; *NB = 1;
+    return;
+  }
   if (H == 1) {
     tw = W < 128 ? W : 128;
     th = 1;
@@ -439,10 +456,12 @@ static void conv_tile_shape(int H, int W, int* TW, int* TH, int* NB) {
 
 // number of pixel tiles per sample the stats buffer must hold: stats is [N][tiles][Cout/2][2] floats.
 // For layers whose tile spans several samples (NB>1) the kernel writes one slot per epilogue warp (4).
-ASYRP_API int asyrp_conv_stats_tiles(int H, int W, int Cout) {
+// `halo`: the conv producing the statistics contains a 3x3 stride-1 segment (tile geometry depends on it)
+ASYRP_API int asyrp_conv_stats_tiles(int H, int W, int Cout, int has_3x3) {
   int TW, TH, NB;
-  conv_tile_shape(H, W, &TW, &TH, &NB);
-  const int tht = TH * conv_mt(H, W, Cout);
+  const int halo = has_3x3 && conv_halo_ok(H, W);
+  conv_tile_shape(H, W, halo, &TW, &TH, &NB);
+  const int tht = TH * conv_mt(H, W, Cout, halo);
   const int tiles = ((W + TW - 1) / TW) * ((H + tht - 1) / tht);
   return NB == 1 ? tiles : tiles * 4;
 }
@@ -455,11 +474,14 @@ ASYRP_API int asyrp_conv_create(const AsyrpConvDesc* d, void** out_op) {
   ConvParams& p = op->p;
   memset(&p, 0, sizeof(p));
   p.N = d->N; p.H = d->H; p.W = d->W; p.Cout = d->Cout;
-  conv_tile_shape(d->H, d->W, &p.TW, &p.TH, &p.NB);
+  bool has3 = false;
+  for (int s = 0; s < d->nseg; ++s) has3 = has3 || d->seg[s].mode == 1;
+  const int halo = has3 && conv_halo_ok(d->H, d->W);
+  conv_tile_shape(d->H, d->W, halo, &p.TW, &p.TH, &p.NB);
   ASYRP_REQUIRE(p.TW * p.TH * p.NB == 128, "asyrp_conv_create: cannot tile H=%d W=%d into 128 pixels", d->H,
                 d->W);
   ASYRP_REQUIRE(!(d->weight_batched && p.NB != 1), "asyrp_conv_create: batched weights need NB==1");
-  op->MT = p.MT = conv_mt(d->H, d->W, d->Cout);
+  op->MT = p.MT = conv_mt(d->H, d->W, d->Cout, halo);
   const int THT = p.TH * p.MT;
   p.tiles_x = (d->W + p.TW - 1) / p.TW;
   p.tiles_y = (d->H + THT - 1) / THT;
@@ -475,8 +497,9 @@ ASYRP_API int asyrp_conv_create(const AsyrpConvDesc* d, void** out_op) {
     const AsyrpConvSeg& sg = d->seg[s];
     ASYRP_REQUIRE(sg.C % 64 == 0 && sg.C > 0, "asyrp_conv_create: segment channels %d not a multiple of 64", sg.C);
     ASYRP_REQUIRE(sg.mode >= 0 && sg.mode <= 2, "asyrp_conv_create: bad segment mode %d", sg.mode);
+    const int mode = (sg.mode == 1 && halo) ? 3 : sg.mode;
     p.seg[s].nchunks = sg.C / 64;
-    p.seg[s].mode = sg.mode;
+    p.seg[s].mode = mode;
     p.seg[s].kbase = ktot;
     p.seg[s].C = sg.C;
     ktot += (sg.mode == 0 ? 1 : 9) * sg.C;
@@ -488,7 +511,8 @@ ASYRP_API int asyrp_conv_create(const AsyrpConvDesc* d, void** out_op) {
       const uint64_t H = d->H, W = d->W;
       dims[0] = C; dims[1] = W; dims[2] = d->N; dims[3] = 1; dims[4] = H;
       strides[0] = C * 2; strides[1] = H * W * C * 2; strides[2] = W * C * 2; strides[3] = W * C * 2;
-      box[0] = 64; box[1] = p.TW; box[2] = p.NB; box[3] = 1; box[4] = sg.mode == 1 ? THT + 2 : THT;
+      box[0] = 64; box[1] = mode == 3 ? p.TW + 2 : p.TW; box[2] = p.NB; box[3] = 1;
+      box[4] = (mode == 1 || mode == 3) ? THT + 2 : THT;
     } else {
       const uint64_t Hi = 2 * d->H, Wi = 2 * d->W;
       dims[0] = 2 * C; dims[1] = Wi / 2; dims[2] = d->N; dims[3] = 2; dims[4] = Hi / 2;
@@ -509,11 +533,13 @@ ASYRP_API int asyrp_conv_create(const AsyrpConvDesc* d, void** out_op) {
     if (rc != ASYRP_OK) { delete op; return rc; }
   }
   p.b_batched = d->weight_batched;
-  p.a_stage_bytes = (any3 ? THT + 2 : THT) * p.row_bytes;
+  p.a_stage_bytes = halo ? (((THT + 2) * (p.TW + 2) * 128u + 1023u) / 1024u) * 1024u
+                         : (any3 ? THT + 2 : THT) * p.row_bytes;
   // shared memory budget: ~205 KB of operand rings
   const uint32_t b_stage = op->BN * 128;
-  p.a_stages = p.MT == 2 ? 3 : 4;
+  p.a_stages = (p.MT == 2 || halo) ? 3 : 4;
   p.b_stages = op->BN == 256 ? 4 : 6;
+  if (halo && op->BN == 128) p.b_stages = 4;
   while (p.a_stages * p.a_stage_bytes + p.b_stages * b_stage > 210 * 1024 && p.a_stages > 2) --p.a_stages;
   while (p.a_stages * p.a_stage_bytes + p.b_stages * b_stage > 210 * 1024 && p.b_stages > 2) --p.b_stages;
   p.ebias = d->ebias;

@@ -123,11 +123,15 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (rows of 128 B, 8-row atoms of 1024 B).
 // Field layout follows the PTX ISA "tcgen05 shared memory descriptor": start>>4 [0,14), LBO>>4 [16,30),
 // SBO>>4 [32,46), version=1 [46,48), base_offset [49,52), layout_type [61,64) (2 = SWIZZLE_128B).
-__device__ __forceinline__ uint64_t umma_desc_k128(uint32_t smem_addr) {
+// sbo_bytes: distance between consecutive 8-row groups (1024 for a dense tile; (TW+2)*128 when the rows are the
+// pixels of a halo tile whose image rows are TW+2 pixels apart).  The 128B swizzle is a function of the shared
+// memory ADDRESS bits (chunk ^= (addr >> 7) & 7), so start addresses need only be 16B-aligned as long as the data
+// was written with the same address-based pattern (TMA does, given a 1024B-aligned box base).
+__device__ __forceinline__ uint64_t umma_desc_k128(uint32_t smem_addr, uint32_t sbo_bytes = 1024) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
   d |= static_cast<uint64_t>(1) << 16;            // LBO (unused for swizzled K-major)
-  d |= static_cast<uint64_t>(1024 >> 4) << 32;    // SBO = 1024 B between 8-row groups
+  d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;  // SBO: bytes between 8-row groups
   d |= static_cast<uint64_t>(1) << 46;            // descriptor version (Blackwell)
   d |= static_cast<uint64_t>(2) << 61;            // SWIZZLE_128B
   return d;

@@ -203,11 +203,11 @@ class Plan:
         """append one kernel launch; kind / algorithmic flops / algorithmic HBM bytes feed bench.py's roofline"""
         self._cur.append(Launch(fn, kind, flops, nbytes))
 
-    def _act(self, H, W, C, stats=True):
+    def _act(self, H, W, C, stats=False, has_3x3=False):
         t = self.pool.alloc((self.N, H, W, C), torch.float16)
         st = None
         if stats:
-            st = self.pool.alloc((self.N, ops.conv_stats_tiles(H, W, C), C // 2, 2), torch.float32)
+            st = self.pool.alloc((self.N, ops.conv_stats_tiles(H, W, C, has_3x3), C // 2, 2), torch.float32)
         return Act(t, st)
 
     def _free(self, act):
@@ -242,7 +242,7 @@ class Plan:
               acc_scale=1.0, stats=True, planar=None, algo_flops=None):
         out = None
         if planar is None:
-            out = self._act(H, W, Cout, stats=stats)
+            out = self._act(H, W, Cout, stats=stats, has_3x3=any(m == MODE_3x3 for _, m in segs))
         op = ops.ConvOp([(s.t, m) for s, m in segs], weight, out=out.t if out else None, ebias=ebias,
                         ebias_stride=ebias_stride, residual=residual.t if residual is not None else None,
                         res_scale=res_scale, acc_scale=acc_scale, stats=out.stats if out else None,

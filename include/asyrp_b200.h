@@ -62,12 +62,14 @@ typedef struct AsyrpConvDesc {
   const void* residual;  /* fp16 NHWC [N][H][W][Cout] or NULL */
   float res_scale, acc_scale;
   void* out;             /* fp16 NHWC [N][H][W][Cout] (ignored when out_planar != NULL) */
-  float* stats;          /* [N][asyrp_conv_stats_tiles(H,W,Cout)][Cout/2][2] fp32 (sum, sum of squares) or NULL */
+  float* stats;          /* [N][asyrp_conv_stats_tiles(..)][Cout/2][2] fp32 (sum, sum of squares) or NULL */
   float* out_planar;     /* optional fp32 NCHW [N][planar_c][H][W]: output channels [0, planar_c<=8) only */
   int planar_c;
 } AsyrpConvDesc;
 
-int asyrp_conv_stats_tiles(int H, int W, int Cout);
+/* number of tile slots of the stats buffer of a conv with this output geometry; has_3x3: the conv has an
+ * ASYRP_CONV_3x3 segment (selects the 8x16 halo tile geometry when H%16==0 and W%8==0) */
+int asyrp_conv_stats_tiles(int H, int W, int Cout, int has_3x3);
 int asyrp_conv_create(const AsyrpConvDesc* desc, void** op); /* encodes TMA descriptors; host only */
 int asyrp_conv_launch(void* op, void* stream);
 int asyrp_conv_set_scales(void* op, float acc_scale, float res_scale); /* hs_coeff of forward(), diffusion.py:512-516 */

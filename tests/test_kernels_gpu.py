@@ -56,7 +56,7 @@ def test_conv3x3_bias_residual_stats(cuda_device, N, H, W, Cin, Cout):
     ref = F.conv2d(_h(x), _h(w), padding=1) + eb.double()[:, :, None, None]
     ref = 0.75 * ref + 1.5 * _h(res)
     out = torch.empty(N, H, W, Cout, dtype=torch.float16, device=cuda_device)
-    stats = ops.new_stats(N, H, W, Cout, cuda_device)
+    stats = ops.new_stats(N, H, W, Cout, cuda_device, True)
     op = ops.ConvOp([(_nhwc_half(x, cuda_device), ops.MODE_3x3)], ops.pack_conv_weight(w).to(cuda_device), out=out,
                     ebias=eb.to(cuda_device), ebias_stride=Cout, residual=_nhwc_half(res, cuda_device),
                     res_scale=1.5, acc_scale=0.75, stats=stats)
@@ -169,7 +169,7 @@ def test_groupnorm_finalize_and_apply(cuda_device, Ca, Cb, resample, act):
         w = _rand((Cs, 64, 1, 1), g, 0.2)
         b = _rand((Cs,), g)
         out = torch.empty(N, H, W, Cs, dtype=torch.float16, device=cuda_device)
-        st = ops.new_stats(N, H, W, Cs, cuda_device)
+        st = ops.new_stats(N, H, W, Cs, cuda_device, False)
         ops.ConvOp([(_nhwc_half(xin, cuda_device), ops.MODE_1x1)], ops.pack_conv_weight(w).to(cuda_device), out=out,
                    ebias=b.to(cuda_device), stats=st).launch()
         srcs.append(out)
