@@ -13,7 +13,8 @@ c_void_p, c_int, c_float = C.c_void_p, C.c_int, C.c_float
 
 
 class AsyrpConvSeg(C.Structure):
-    _fields_ = [("src", c_void_p), ("C", c_int), ("mode", c_int)]
+    _fields_ = [("src", c_void_p), ("C", c_int), ("mode", c_int), ("affine", c_void_p), ("affine_stride", c_int),
+                ("act", c_int)]
 
 
 class AsyrpConvDesc(C.Structure):

@@ -27,7 +27,7 @@
 namespace asyrp {
 
 static constexpr int kMaxSeg = 3;
-static constexpr int kNumThreads = 192;
+static constexpr int kNumThreads = 320;  // + 4 transform warps (6..9)
 
 struct ConvSegDev {
   int nchunks;  // C / 64
@@ -35,6 +35,11 @@ struct ConvSegDev {
                 // 3: 3x3 stride 1 from ONE halo tile (TW == 8: every tap is an address offset into it)
   int kbase;    // first K column of this segment in the weight matrix
   int C;        // channels of the source
+  // optional in-place operand transform  x -> act(a*x + b)  (GroupNorm apply + SiLU), applied to the A tile in
+  // shared memory between the TMA load and the MMA; out-of-image pixels stay exactly zero (the conv's padding)
+  const float* affine;  // [N][aff_stride] floats: (a, b) pairs of this segment's channels, or nullptr
+  int aff_stride;
+  int act;              // 1: SiLU after the affine
 };
 
 struct ConvParams {
@@ -58,6 +63,7 @@ struct ConvParams {
   int planar_c;
   float* stats;            // [N][tiles_y*tiles_x][Cout/2][2] partial (sum, sumsq) or nullptr
   int b_batched;           // weights have a per-sample batch dimension (attention GEMMs)
+  int any_transform;       // some segment has an affine: the MMA warp then waits on readyA instead of fullA
 };
 
 template <int BN, int MT>
@@ -77,7 +83,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
   uint64_t* bars = reinterpret_cast<uint64_t*>(sB + p.b_stages * kBStage);
   uint64_t* fullA = bars;
   uint64_t* emptyA = fullA + p.a_stages;
-  uint64_t* fullB = emptyA + p.a_stages;
+  uint64_t* readyA = emptyA + p.a_stages;
+  uint64_t* fullB = readyA + p.a_stages;
   uint64_t* emptyB = fullB + p.b_stages;
   uint64_t* tfull = emptyB + p.b_stages;
   uint64_t* tempty = tfull + 2;
@@ -89,6 +96,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
     for (int i = 0; i < p.a_stages; ++i) {
       mbar_init(&fullA[i], 1);
       mbar_init(&emptyA[i], 1);
+      mbar_init(&readyA[i], 4);
     }
     for (int i = 0; i < p.b_stages; ++i) {
       mbar_init(&fullB[i], 1);
@@ -185,7 +193,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
           const uint32_t sub_stride = sg.mode == 3 ? p.TH * halo_pitch : p.TH * p.row_bytes;
           for (int ch = 0; ch < sg.nchunks; ++ch) {
             for (int cp = 0; cp < ncopies; ++cp) {
-              mbar_wait(&fullA[sa], pa);
+              mbar_wait(p.any_transform ? &readyA[sa] : &fullA[sa], pa);
               tc_fence_after();
               const uint32_t a_base = smem_u32(sA + sa * p.a_stage_bytes);
               for (int tp = 0; tp < ntaps; ++tp) {
@@ -215,6 +223,83 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
       }
     }
     __syncwarp();
+  } else if (warp >= 6) {
+    // ======================================================== operand transform (warps 6..9), in place
+    if (p.any_transform) {
+      const int tt = threadIdx.x - 6 * 32;   // 0..127
+      const int jl = tt & 7;                  // logical 16B chunk = channels [jl*8, jl*8+8) of the 64-channel slab
+      const int pl = tt >> 3;                 // pixel lane 0..15
+      int sa = 0;
+      uint32_t pa = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int mt = tile % p.m_tiles;
+        const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, tn = mt / (p.tiles_x * p.tiles_y);
+        const int x0 = tx * p.TW, y0 = ty * THT, n0 = tn * p.NB;
+        for (int s = 0; s < p.nseg; ++s) {
+          const ConvSegDev sg = p.seg[s];
+          const int ncopies = (sg.mode == 0 || sg.mode == 3) ? 1 : (sg.mode == 1 ? 3 : 9);
+          const int pw = sg.mode == 3 ? p.TW + 2 : p.TW;
+          const int rows = (sg.mode == 1 || sg.mode == 3) ? THT + 2 : THT;
+          const int npix = rows * p.NB * pw;
+          const int yoff = (sg.mode == 1 || sg.mode == 3) ? -1 : 0;
+          for (int ch = 0; ch < sg.nchunks; ++ch) {
+            float ca[8], cb[8];
+            if (sg.affine != nullptr && p.NB == 1) {
+              const float4* ap = reinterpret_cast<const float4*>(
+                  sg.affine + static_cast<size_t>(n0 < p.N ? n0 : 0) * sg.aff_stride + (ch * 64 + jl * 8) * 2);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float4 t4 = ap[k];
+                ca[2 * k] = t4.x; cb[2 * k] = t4.y; ca[2 * k + 1] = t4.z; cb[2 * k + 1] = t4.w;
+              }
+            }
+            for (int cp = 0; cp < ncopies; ++cp) {
+              mbar_wait(&fullA[sa], pa);
+              if (sg.affine != nullptr) {
+                uint8_t* stage = sA + sa * p.a_stage_bytes;
+                const int xoff = sg.mode == 3 ? -1 : (sg.mode == 1 ? cp - 1 : 0);
+                for (int px = pl; px < npix; px += 16) {
+                  const int xx = px % pw, r2 = px / pw;
+                  const int nn = r2 % p.NB, hy = r2 / p.NB;
+                  const int x = x0 + xx + xoff, y = y0 + hy + yoff, n = n0 + nn;
+                  uint4* slot = reinterpret_cast<uint4*>(stage + px * 128 + ((jl ^ (px & 7)) << 4));
+                  uint4 u = make_uint4(0u, 0u, 0u, 0u);
+                  if (x >= 0 && x < p.W && y >= 0 && y < p.H && n < p.N) {
+                    if (p.NB != 1) {
+                      const float4* ap = reinterpret_cast<const float4*>(
+                          sg.affine + static_cast<size_t>(n) * sg.aff_stride + (ch * 64 + jl * 8) * 2);
+#pragma unroll
+                      for (int k = 0; k < 4; ++k) {
+                        const float4 t4 = ap[k];
+                        ca[2 * k] = t4.x; cb[2 * k] = t4.y; ca[2 * k + 1] = t4.z; cb[2 * k + 1] = t4.w;
+                      }
+                    }
+                    u = *slot;
+                    __half2* h2 = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                      float2 f = __half22float2(h2[k]);
+                      f.x = fmaf(ca[2 * k], f.x, cb[2 * k]);
+                      f.y = fmaf(ca[2 * k + 1], f.y, cb[2 * k + 1]);
+                      if (sg.act) {
+                        f.x = __fdividef(f.x, 1.0f + __expf(-f.x));
+                        f.y = __fdividef(f.y, 1.0f + __expf(-f.y));
+                      }
+                      h2[k] = __floats2half2_rn(f.x, f.y);
+                    }
+                  }
+                  *slot = u;
+                }
+                fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+              }
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&readyA[sa]);
+              if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
+            }
+          }
+        }
+      }
+    }
   } else {
     // ======================================================== epilogue (warps 2..5)
     const int q = warp & 3;  // TMEM lane quarter this warp may access
@@ -398,6 +483,10 @@ struct AsyrpConvSeg {
   const void* src;  // fp16 NHWC source tensor
   int C;            // its channel count (multiple of 64)
   int mode;         // 0: 1x1, 1: 3x3 s1 p1, 2: 3x3 s2 pad(0,1,0,1) (source is [N][2H][2W][C])
+  const float* affine;  // optional fused GroupNorm-apply: (a, b) pairs of this segment's channels, row n at
+                        // affine + n*affine_stride floats; the operand becomes act(a*x + b)
+  int affine_stride;
+  int act;              // 1: SiLU
 };
 
 struct AsyrpConvDesc {
@@ -502,6 +591,11 @@ ASYRP_API int asyrp_conv_create(const AsyrpConvDesc* d, void** out_op) {
     p.seg[s].mode = mode;
     p.seg[s].kbase = ktot;
     p.seg[s].C = sg.C;
+    p.seg[s].affine = sg.affine;
+    p.seg[s].aff_stride = sg.affine_stride;
+    p.seg[s].act = sg.act;
+    ASYRP_REQUIRE(!(sg.affine != nullptr && sg.mode == 2), "asyrp_conv_create: no fused affine on stride-2 segments");
+    if (sg.affine != nullptr) p.any_transform = 1;
     ktot += (sg.mode == 0 ? 1 : 9) * sg.C;
     any3 = any3 || sg.mode == 1;
     uint64_t dims[5], strides[4];
@@ -554,7 +648,7 @@ ASYRP_API int asyrp_conv_create(const AsyrpConvDesc* d, void** out_op) {
   p.out = static_cast<__half*>(d->out);
   p.stats = d->stats;
   op->smem_bytes = 1024 + static_cast<size_t>(p.a_stages) * p.a_stage_bytes +
-                   static_cast<size_t>(p.b_stages) * b_stage + (2 * (p.a_stages + p.b_stages) + 4) * 8 + 16 +
+                   static_cast<size_t>(p.b_stages) * b_stage + (3 * p.a_stages + 2 * p.b_stages + 4) * 8 + 16 +
                    2 * 4 * op->BN * 4;
   ASYRP_REQUIRE(op->smem_bytes <= 227 * 1024, "asyrp_conv_create: smem %zu too large", op->smem_bytes);
   const int sms = sm_count();

@@ -242,52 +242,67 @@ class Plan:
               acc_scale=1.0, stats=True, planar=None, algo_flops=None):
         out = None
         if planar is None:
-            out = self._act(H, W, Cout, stats=stats, has_3x3=any(m == MODE_3x3 for _, m in segs))
-        op = ops.ConvOp([(s.t, m) for s, m in segs], weight, out=out.t if out else None, ebias=ebias,
+            out = self._act(H, W, Cout, stats=stats, has_3x3=any(sg[1] == MODE_3x3 for sg in segs))
+        segs = [tuple(sg) + (None, 0, 0) * (len(sg) == 2) for sg in segs]
+        op = ops.ConvOp([(sg[0].t,) + sg[1:] for sg in segs], weight, out=out.t if out else None, ebias=ebias,
                         ebias_stride=ebias_stride, residual=residual.t if residual is not None else None,
                         res_scale=res_scale, acc_scale=acc_scale, stats=out.stats if out else None,
                         out_planar=planar, out_shape=(self.N, H, W, Cout))
         ktot = weight.shape[-1]
         flops = algo_flops if algo_flops is not None else 2.0 * self.N * H * W * Cout * ktot
-        nbytes = 2.0 * (sum(s.t.numel() for s, _ in segs) + weight.numel() + self.N * H * W * Cout
+        nbytes = 2.0 * (sum(sg[0].t.numel() for sg in segs) + weight.numel() + self.N * H * W * Cout
                         + (residual.t.numel() if residual is not None else 0))
         self._emit(op.launch, "conv", flops, nbytes)
         return out, op
 
     # ------------------------------------------------------------------ blocks
+    @staticmethod
+    def _fused(srcs, mode, aff, act):
+        """conv segments over the channel concat of `srcs` with the GroupNorm affine (+SiLU) fused into the operand"""
+        segs, off = [], 0
+        for s_ in srcs:
+            segs.append((s_, mode, aff, off, act))
+            off += s_.C
+        return segs
+
     def _res_block(self, layer: Res, srcs):
+        """ResnetBlock (ddpm/diffusion.py:151-170) / ResBlock (improved_ddpm/unet.py:278-298): two fused
+        GN-apply+SiLU+conv3x3 launches; the 1x1 shortcut is extra K of the second; the block input is read raw."""
         eng, W = self.eng, self.eng.W
         p, ddpm = layer.name, self.eng.arch.family == "ddpm"
         eoff = eng.emb_off[p]
         mode = {"none": RESAMPLE_NONE, "up": RESAMPLE_UP2, "down": RESAMPLE_AVGPOOL2}[layer.resample]
         aff1 = self._gn(srcs, W[p + ".g1"], W[p + ".be1"])
-        a1 = self._apply(srcs, aff1, 1, mode)
-        self.pool.release(aff1)
-        xr = None
-        if mode != RESAMPLE_NONE:  # ADM up/down block resamples the skip branch too (unet.py:279-284)
+        xr, a1 = None, None
+        if mode != RESAMPLE_NONE:
+            # ADM up/down block: the resample sits between SiLU and the conv, and the skip branch is resampled too
+            # (unet.py:279-284) -> materialise both with the pointwise kernel
+            a1 = self._apply(srcs, aff1, 1, mode)
             xr = self._apply(srcs, None, 0, mode)
-        H, Wd = a1.H, a1.W
+            segs1, H, Wd = [(a1, MODE_3x3)], a1.H, a1.W
+        else:
+            segs1, H, Wd = self._fused(srcs, MODE_3x3, aff1, 1), srcs[0].H, srcs[0].W
         if ddpm:
-            h, _ = self._conv([(a1, MODE_3x3)], W[p + ".w1"], layer.cout, H, Wd,
+            h, _ = self._conv(segs1, W[p + ".w1"], layer.cout, H, Wd,
                               ebias=self.emb_all[:, eoff:eoff + layer.cout], ebias_stride=eng.emb_total)
-            self._free(a1)
             aff2 = self._gn([h], W[p + ".g2"], W[p + ".be2"])
         else:
-            h, _ = self._conv([(a1, MODE_3x3)], W[p + ".w1"], layer.cout, H, Wd, ebias=W[p + ".b1"])
-            self._free(a1)
+            h, _ = self._conv(segs1, W[p + ".w1"], layer.cout, H, Wd, ebias=W[p + ".b1"])
             # GN(h)*(1+scale)+shift, [scale | shift] = Linear(SiLU(emb))  (unet.py:287-294)
             aff2 = self._gn([h], W[p + ".g2"], W[p + ".be2"], self.emb_all[:, eoff:eoff + 2 * layer.cout],
                             eng.emb_total)
-        a2 = self._apply([h], aff2, 1)
-        self.pool.release(aff2)
-        self._free(h)
+        self.pool.release(aff1)
+        if a1 is not None:
+            self._free(a1)
+        segs2 = self._fused([h], MODE_3x3, aff2, 1)
         if layer.cin != layer.cout:
-            segs = [(a2, MODE_3x3)] + [(s, MODE_1x1) for s in srcs]
-            out, _ = self._conv(segs, W[p + ".w2"], layer.cout, H, Wd, ebias=W[p + ".b2"])
+            out, _ = self._conv(segs2 + [(s_, MODE_1x1) for s_ in srcs], W[p + ".w2"], layer.cout, H, Wd,
+                                ebias=W[p + ".b2"])
         else:
             resid = xr if xr is not None else srcs[0]
-            out, _ = self._conv([(a2, MODE_3x3)], W[p + ".w2"], layer.cout, H, Wd, ebias=W[p + ".b2"], residual=resid)
-        self._free(a2)
+            out, _ = self._conv(segs2, W[p + ".w2"], layer.cout, H, Wd, ebias=W[p + ".b2"], residual=resid)
+        self.pool.release(aff2)
+        self._free(h)
         if xr is not None:
             self._free(xr)
         return out
@@ -298,10 +313,9 @@ class Plan:
         d = a_.head_ch if a_.head_ch else C
         heads = C // d
         aff = self._gn([x], W[p + ".g"], W[p + ".be"])
-        xn = self._apply([x], aff, 0)
+        qkv, _ = self._conv(self._fused([x], MODE_1x1, aff, 0), W[p + ".wqkv"], 3 * C, x.H, x.W, ebias=W[p + ".bqkv"],
+                            stats=False)
         self.pool.release(aff)
-        qkv, _ = self._conv([(xn, MODE_1x1)], W[p + ".wqkv"], 3 * C, x.H, x.W, ebias=W[p + ".bqkv"], stats=False)
-        self._free(xn)
         att = self._act(x.H, x.W, C, stats=False)
         N, T = self.N, x.H * x.W
         scale = float(d) ** -0.5  # C^-0.5 (ddpm/diffusion.py:213) == (d^-1/4)^2 (improved_ddpm/unet.py:389-392)
@@ -391,32 +405,32 @@ class Plan:
         eng, a, W = self.eng, self.eng.arch, self.eng.W
         p, C = f"layer_{i}", a.mid_ch
         eoff = eng.emb_off[p]
-        src = h
+        seg1 = [(h, MODE_1x1)]
+        aff1 = None
         if a.family == "adm":  # GN, SiLU before the first 1x1 conv (improved_ddpm/unet.py:821-825)
-            aff = self._gn([h], W[p + ".g1"], W[p + ".be1"])
-            src = self._apply([h], aff, 1)
-            self.pool.release(aff)
+            aff1 = self._gn([h], W[p + ".g1"], W[p + ".be1"])
+            seg1 = self._fused([h], MODE_1x1, aff1, 1)
         # two variants of the first conv: with the timestep projection (default) and without (ignore_timestep)
-        d1, op_t = self._conv([(src, MODE_1x1)], W[p + ".w1"], C, h.H, h.W,
-                              ebias=self.emb_all[:, eoff:eoff + C], ebias_stride=eng.emb_total)
+        d1, op_t = self._conv(seg1, W[p + ".w1"], C, h.H, h.W, ebias=self.emb_all[:, eoff:eoff + C],
+                              ebias_stride=eng.emb_total)
         self._cur.pop()
-        op_nt = ops.ConvOp([(src.t, MODE_1x1)], W[p + ".w1"], out=d1.t, ebias=W[p + ".b1"], stats=d1.stats)
+        op_nt = ops.ConvOp([(sg[0].t,) + tuple(sg[1:]) for sg in seg1], W[p + ".w1"], out=d1.t, ebias=W[p + ".b1"],
+                           stats=d1.stats)
         st = self.eng.state
         self._emit(lambda: (op_nt if st["ignore_timestep"] else op_t).launch(), "conv",
                    2.0 * self.N * h.H * h.W * C * C)
-        if src is not h:
-            self._free(src)
+        if aff1 is not None:
+            self.pool.release(aff1)
         aff = self._gn([d1], W[p + ".g2"], W[p + ".be2"])
-        a2 = self._apply([d1], aff, 1)
-        self.pool.release(aff)
-        self._free(d1)
+        seg2 = self._fused([d1], MODE_1x1, aff, 1)
         if last:  # API-visible delta_h = output of the last DeltaBlock
-            dh, _ = self._conv([(a2, MODE_1x1)], W[p + ".w2"], C, h.H, h.W, ebias=W[p + ".b2"], stats=False)
+            dh, _ = self._conv(seg2, W[p + ".w2"], C, h.H, h.W, ebias=W[p + ".b2"], stats=False)
             self.delta_h = dh
         # h2 = c_{i+1} * (conv2(a2) + b2) + (c0*h | 1*h2_prev), with GroupNorm partial sums for the decoder
-        h2, op = self._conv([(a2, MODE_1x1)], W[p + ".w2"], C, h.H, h.W, ebias=W[p + ".b2"], residual=h2_prev)
+        h2, op = self._conv(seg2, W[p + ".w2"], C, h.H, h.W, ebias=W[p + ".b2"], residual=h2_prev)
         self.scale_ops.append((op, i))
-        self._free(a2)
+        self.pool.release(aff)
+        self._free(d1)
         if h2_prev is not h:
             self._free(h2_prev)
         return h2
@@ -429,12 +443,10 @@ class Plan:
             h = self._run_stage(stage, h, skip=self.hs[idx], keep_input=(si == 0))
             idx -= 1
         aff = self._gn([h], W["norm_out.g"], W["norm_out.be"])
-        an = self._apply([h], aff, 1)
+        self._conv(self._fused([h], MODE_3x3, aff, 1), W["conv_out.w"], 64, h.H, h.W, ebias=W["conv_out.b"],
+                   stats=False, planar=out_planar, algo_flops=2.0 * self.N * h.H * h.W * a.out_ch * 9 * h.C)
         self.pool.release(aff)
         self._free(h)
-        self._conv([(an, MODE_3x3)], W["conv_out.w"], 64, an.H, an.W, ebias=W["conv_out.b"], stats=False,
-                   planar=out_planar, algo_flops=2.0 * self.N * an.H * an.W * a.out_ch * 9 * an.C)
-        self._free(an)
 
     # ------------------------------------------------------------------ execution
     def set_coeffs(self, hs_coeff):

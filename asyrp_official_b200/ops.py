@@ -52,15 +52,19 @@ def new_stats(N, H, W, C, device, has_3x3):
 class ConvOp:
     """One implicit-GEMM convolution launch (asyrp_conv_create / asyrp_conv_launch).
 
-    segs: list of (src NHWC fp16 tensor, mode).  The output is [N][H][W][Cout]; for MODE_3x3_S2 the source is
-    [N][2H][2W][C].  weight: packed fp16 [Cout][K] ([N][Cout][K] when weight_batched).
+    segs: list of (src NHWC fp16 tensor, mode) or (src, mode, affine, affine_offset_channels, act): with an affine
+    table ([N][Ctot][2] fp32, GroupNorm finalise output) the operand becomes act(a*x + b), applied in shared memory
+    inside the kernel (the activated tensor is never materialised).  The output is [N][H][W][Cout]; for MODE_3x3_S2
+    the source is [N][2H][2W][C].  weight: packed fp16 [Cout][K] ([N][Cout][K] when weight_batched).
     """
 
     def __init__(self, segs, weight, out=None, ebias=None, ebias_stride=0, residual=None, res_scale=1.0,
                  acc_scale=1.0, stats=None, out_planar=None, out_shape=None, weight_batched=False):
         lib = _lib.load()
-        srcs = [s for s, _ in segs]
-        _need_cuda(*srcs, weight, out, ebias, residual, stats, out_planar)
+        segs = [tuple(sg) + (None, 0, 0) * (len(sg) == 2) for sg in segs]
+        srcs = [sg[0] for sg in segs]
+        affs = [sg[2] for sg in segs]
+        _need_cuda(*srcs, *affs, weight, out, ebias, residual, stats, out_planar)
         if out is not None:
             N, H, W, Cout = out.shape
         else:
@@ -69,11 +73,16 @@ class ConvOp:
         d.N, d.H, d.W, d.Cout = N, H, W, Cout
         d.nseg = len(segs)
         ktot = 0
-        for i, (src, mode) in enumerate(segs):
+        for i, (src, mode, aff, aff_off, act) in enumerate(segs):
             assert src.dtype == torch.float16 and src.is_contiguous()
             d.seg[i].src = src.data_ptr()
             d.seg[i].C = src.shape[-1]
             d.seg[i].mode = mode
+            if aff is not None:
+                assert aff.dtype == torch.float32 and aff.is_contiguous() and aff.shape[-1] == 2
+                d.seg[i].affine = aff.data_ptr() + aff_off * 2 * 4
+                d.seg[i].affine_stride = aff.shape[1] * 2
+                d.seg[i].act = int(act)
             ktot += (1 if mode == MODE_1x1 else 9) * src.shape[-1]
         assert weight.dtype == torch.float16 and weight.is_contiguous() and weight.shape[-1] == ktot, \
             (weight.shape, ktot)
@@ -90,7 +99,7 @@ class ConvOp:
             assert out_planar.dtype == torch.float32
             d.out_planar = out_planar.data_ptr()
             d.planar_c = out_planar.shape[1]
-        self._keep = (srcs, weight, out, ebias, residual, stats, out_planar)
+        self._keep = (srcs, affs, weight, out, ebias, residual, stats, out_planar)
         h = C.c_void_p()
         check(lib.asyrp_conv_create(C.byref(d), C.byref(h)), "asyrp_conv_create")
         self._h = h

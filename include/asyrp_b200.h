@@ -48,6 +48,14 @@ typedef struct AsyrpConvSeg {
   const void* src; /* fp16 NHWC source */
   int C;           /* channels, multiple of 64 */
   int mode;        /* ASYRP_CONV_* */
+  /* optional fused GroupNorm-apply (+SiLU) on this operand: x -> act(a*x + b), evaluated in shared memory between
+   * the TMA load and the MMA (norm1/norm2 + nonlinearity of ResnetBlock, ddpm/diffusion.py:153-161; in_layers /
+   * out_layers of ResBlock, improved_ddpm/unet.py:224-228,248-255).  affine: fp32 (a, b) pairs of this segment's
+   * channels, row n at affine + n*affine_stride floats (output of asyrp_gn_finalize, offset to the segment's first
+   * channel); NULL = raw operand.  Zero padding is applied AFTER the transform, as the reference's convs see it. */
+  const float* affine;
+  int affine_stride;
+  int act;         /* 1: SiLU after the affine */
 } AsyrpConvSeg;
 
 typedef struct AsyrpConvDesc {

@@ -274,3 +274,39 @@ def test_pack_embedding_linear_ddim(cuda_device):
     ops.ddim_update(xt.to(dev), et6.to(dev), em6.to(dev), z.to(dev), o_next, o_x0, at.item(), an.item(), c1.item(),
                     c2.item())
     assert (o_next.cpu() - nxt1).abs().max().item() <= 1e-6
+
+
+@pytest.mark.parametrize("N,H,W,C1,C2,Cout,mode,act", [(2, 32, 32, 128, 0, 128, "3x3", 1), (2, 32, 32, 128, 64, 128, "3x3", 1),
+                                                       (3, 8, 8, 128, 64, 128, "3x3", 1), (2, 16, 16, 128, 0, 384, "1x1", 0),
+                                                       (1, 64, 64, 64, 0, 256, "3x3", 1), (2, 16, 24, 64, 64, 64, "3x3", 1)])
+def test_conv_with_fused_groupnorm_silu_operand(cuda_device, N, H, W, C1, C2, Cout, mode, act):
+    """conv(act(GroupNorm(cat(x1, x2)))) with the affine + SiLU applied to the operand tile in shared memory
+    (ResnetBlock norm1-swish-conv1 over the decoder's concatenated input, ddpm/diffusion.py:153-155,549).
+    The zero padding must be applied after the activation."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(11)
+    C = C1 + C2
+    xs = [_rand((N, c, H, W), g) * 1.5 + 0.3 for c in (C1, C2) if c]
+    aff = torch.stack([_rand((N, C), g) * 0.5 + 1.0, _rand((N, C), g) * 0.5], dim=-1).contiguous()  # (a, b) pairs
+    k = 3 if mode == "3x3" else 1
+    w = _rand((Cout, C, k, k), g, 1.0 / math.sqrt(k * k * C))
+    b = _rand((Cout,), g)
+    xcat = torch.cat([_h(x) for x in xs], 1)
+    y = xcat * aff[..., 0].double()[:, :, None, None] + aff[..., 1].double()[:, :, None, None]
+    if act:
+        y = y * torch.sigmoid(y)
+    y = _h(y.float())  # the transformed operand is rounded to fp16 before the MMA
+    ref = F.conv2d(y, _h(w), padding=k // 2) + b.double()[None, :, None, None]
+    m = ops.MODE_3x3 if mode == "3x3" else ops.MODE_1x1
+    affd = aff.to(cuda_device)
+    segs, off, wparts = [], 0, []
+    for x in xs:
+        segs.append((_nhwc_half(x, cuda_device), m, affd, off, act))
+        wparts.append(ops.pack_conv_weight(w[:, off:off + x.shape[1]]))
+        off += x.shape[1]
+    out = torch.empty(N, H, W, Cout, dtype=torch.float16, device=cuda_device)
+    op = ops.ConvOp(segs, torch.cat(wparts, 1).contiguous().to(cuda_device), out=out, ebias=b.to(cuda_device))
+    op.launch()
+    op.launch()
+    torch.cuda.synchronize()
+    _check(_from_nhwc(out), ref, 2.5e-3, f"fused gn+silu conv {mode}")
