@@ -19,6 +19,7 @@ class Res:
     cin: int
     cout: int
     resample: str = "none"
+    split: Tuple[int, ...] = ()   # channel counts of the concatenated inputs (decoder: (h, skip)); () = single input
 
 
 @dataclass
@@ -86,7 +87,7 @@ def ddpm_arch(ch=128, out_ch=3, ch_mult=(1, 1, 2, 2, 4, 4), num_res_blocks=2, at
         for b in range(num_res_blocks + 1):
             if b == num_res_blocks:
                 skip_in = ch * in_mult[lvl]
-            stage = [Res(f"up.{lvl}.block.{b}", block_in + skip_in, block_out)]
+            stage = [Res(f"up.{lvl}.block.{b}", block_in + skip_in, block_out, split=(block_in, skip_in))]
             block_in = block_out
             if cur in attn_resolutions:
                 stage.append(Attn(f"up.{lvl}.attn.{b}", block_in))
@@ -133,7 +134,7 @@ def adm_arch(image_size=256, model_channels=128, num_res_blocks=1, attention_res
         for i in range(num_res_blocks + 1):
             ich = chans.pop()
             j = 0
-            stage = [Res(f"output_blocks.{oidx}.{j}", ch + ich, int(mc * m))]
+            stage = [Res(f"output_blocks.{oidx}.{j}", ch + ich, int(mc * m), split=(ch, ich))]
             ch = int(mc * m)
             j += 1
             if ds in attn_ds:

@@ -27,7 +27,8 @@
 namespace asyrp {
 
 static constexpr int kMaxSeg = 3;
-static constexpr int kNumThreads = 320;  // + 4 transform warps (6..9)
+static constexpr int kNumTransformWarps = 8;
+static constexpr int kNumThreads = 192 + 32 * kNumTransformWarps;  // + transform warps (6..13)
 
 struct ConvSegDev {
   int nchunks;  // C / 64
@@ -96,7 +97,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
     for (int i = 0; i < p.a_stages; ++i) {
       mbar_init(&fullA[i], 1);
       mbar_init(&emptyA[i], 1);
-      mbar_init(&readyA[i], 4);
+      mbar_init(&readyA[i], kNumTransformWarps);
     }
     for (int i = 0; i < p.b_stages; ++i) {
       mbar_init(&fullB[i], 1);
@@ -226,9 +227,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
   } else if (warp >= 6) {
     // ======================================================== operand transform (warps 6..9), in place
     if (p.any_transform) {
-      const int tt = threadIdx.x - 6 * 32;   // 0..127
+      constexpr int kLanes = kNumTransformWarps * 4;  // pixels handled concurrently (8 threads per pixel)
+      const int tt = threadIdx.x - 6 * 32;
       const int jl = tt & 7;                  // logical 16B chunk = channels [jl*8, jl*8+8) of the 64-channel slab
-      const int pl = tt >> 3;                 // pixel lane 0..15
+      const int pl = tt >> 3;                 // pixel lane
       int sa = 0;
       uint32_t pa = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -238,9 +240,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
         for (int s = 0; s < p.nseg; ++s) {
           const ConvSegDev sg = p.seg[s];
           const int ncopies = (sg.mode == 0 || sg.mode == 3) ? 1 : (sg.mode == 1 ? 3 : 9);
-          const int pw = sg.mode == 3 ? p.TW + 2 : p.TW;
+          const int pw = sg.mode == 3 ? p.TW + 2 : p.TW;      // pixels per (row, sample) in the stage
+          const int prow = pw * p.NB;                          // pixels per tile row
           const int rows = (sg.mode == 1 || sg.mode == 3) ? THT + 2 : THT;
-          const int npix = rows * p.NB * pw;
+          const int npix = rows * prow;
           const int yoff = (sg.mode == 1 || sg.mode == 3) ? -1 : 0;
           for (int ch = 0; ch < sg.nchunks; ++ch) {
             float ca[8], cb[8];
@@ -258,9 +261,13 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
               if (sg.affine != nullptr) {
                 uint8_t* stage = sA + sa * p.a_stage_bytes;
                 const int xoff = sg.mode == 3 ? -1 : (sg.mode == 1 ? cp - 1 : 0);
-                for (int px = pl; px < npix; px += 16) {
-                  const int xx = px % pw, r2 = px / pw;
-                  const int nn = r2 % p.NB, hy = r2 / p.NB;
+                // (hy, r) = (tile row, position inside the row) of pixel px, advanced incrementally (no divisions)
+                int hy = pl / prow, r = pl - hy * prow;
+                const int dhy = kLanes / prow, dr = kLanes - dhy * prow;
+#pragma unroll 2
+                for (int px = pl; px < npix; px += kLanes) {
+                  int nn = 0, xx = r;
+                  if (p.NB != 1) { nn = r / pw; xx = r - nn * pw; }
                   const int x = x0 + xx + xoff, y = y0 + hy + yoff, n = n0 + nn;
                   uint4* slot = reinterpret_cast<uint4*>(stage + px * 128 + ((jl ^ (px & 7)) << 4));
                   uint4 u = make_uint4(0u, 0u, 0u, 0u);
@@ -289,6 +296,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
                     }
                   }
                   *slot = u;
+                  hy += dhy;
+                  r += dr;
+                  if (r >= prow) { r -= prow; ++hy; }
                 }
                 fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
               }

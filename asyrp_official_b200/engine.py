@@ -117,7 +117,14 @@ def pack_weights(arch: Arch, sd, device, n_delta):
             W[p + ".b1"] = f32(sd[p + c1 + ".bias"])
         W[p + ".g1"], W[p + ".be1"] = f32(sd[p + n1 + ".weight"]), f32(sd[p + n1 + ".bias"])
         W[p + ".g2"], W[p + ".be2"] = f32(sd[p + n2 + ".weight"]), f32(sd[p + n2 + ".bias"])
-        W[p + ".w1"] = pk(sd[p + c1 + ".weight"])
+        # K layout is segment-major: a concatenated input (decoder) is two K-segments, each tap-major over its own
+        # channels, because the conv reads the two source tensors separately (the concat is never materialised)
+        w1 = sd[p + c1 + ".weight"].detach().float()
+        parts, o = [], 0
+        for c_ in (layer.split or (layer.cin,)):
+            parts.append(ops.pack_conv_weight(w1[:, o:o + c_]))
+            o += c_
+        W[p + ".w1"] = torch.cat(parts, dim=1).contiguous().to(device)
         w2 = ops.pack_conv_weight(sd[p + c2 + ".weight"].detach().float())
         b2 = sd[p + c2 + ".bias"].detach().float().cpu()
         if layer.cin != layer.cout:

@@ -278,7 +278,9 @@ def test_pack_embedding_linear_ddim(cuda_device):
 
 @pytest.mark.parametrize("N,H,W,C1,C2,Cout,mode,act", [(2, 32, 32, 128, 0, 128, "3x3", 1), (2, 32, 32, 128, 64, 128, "3x3", 1),
                                                        (3, 8, 8, 128, 64, 128, "3x3", 1), (2, 16, 16, 128, 0, 384, "1x1", 0),
-                                                       (1, 64, 64, 64, 0, 256, "3x3", 1), (2, 16, 24, 64, 64, 64, "3x3", 1)])
+                                                       (1, 64, 64, 64, 0, 256, "3x3", 1), (2, 16, 24, 64, 64, 64, "3x3", 1),
+                                                       (2, 8, 8, 256, 256, 256, "3x3", 1), (2, 8, 8, 256, 0, 256, "3x3", 1),
+                                                       (2, 16, 16, 256, 128, 128, "3x3", 1), (2, 8, 8, 256, 128, 256, "3x3", 1)])
 def test_conv_with_fused_groupnorm_silu_operand(cuda_device, N, H, W, C1, C2, Cout, mode, act):
     """conv(act(GroupNorm(cat(x1, x2)))) with the affine + SiLU applied to the operand tile in shared memory
     (ResnetBlock norm1-swish-conv1 over the decoder's concatenated input, ddpm/diffusion.py:153-155,549).
@@ -310,3 +312,48 @@ def test_conv_with_fused_groupnorm_silu_operand(cuda_device, N, H, W, C1, C2, Co
     op.launch()
     torch.cuda.synchronize()
     _check(_from_nhwc(out), ref, 2.5e-3, f"fused gn+silu conv {mode}")
+
+
+@pytest.mark.parametrize("H,W,C,C1,C2", [(32, 32, 128, 128, 64), (8, 8, 128, 128, 64), (8, 8, 256, 256, 256),
+                                         (16, 16, 256, 256, 128)])
+def test_fused_operand_plus_raw_shortcut_segments(cuda_device, H, W, C, C1, C2):
+    """conv2(silu(gn(h))) + nin_shortcut(cat(x1, x2)): one transformed 3x3 segment and two raw 1x1 segments in the
+    same accumulator (ResnetBlock of the decoder, ddpm/diffusion.py:159-170)"""
+    ops = _ops()
+    g = torch.Generator().manual_seed(12)
+    N = 2
+    h, x1, x2 = _rand((N, C, H, W), g), _rand((N, C1, H, W), g), _rand((N, C2, H, W), g)
+    aff = torch.stack([_rand((N, C), g) * 0.5 + 1.0, _rand((N, C), g) * 0.5], dim=-1).contiguous()
+    w3 = _rand((C, C, 3, 3), g, 1.0 / math.sqrt(9 * C))
+    w1 = _rand((C, C1 + C2, 1, 1), g, 1.0 / math.sqrt(C1 + C2))
+    y = _h(h) * aff[..., 0].double()[:, :, None, None] + aff[..., 1].double()[:, :, None, None]
+    y = _h((y * torch.sigmoid(y)).float())
+    ref = F.conv2d(y, _h(w3), padding=1) + F.conv2d(torch.cat([_h(x1), _h(x2)], 1), _h(w1))
+    wp = torch.cat([ops.pack_conv_weight(w3), ops.pack_conv_weight(w1[:, :C1]), ops.pack_conv_weight(w1[:, C1:])], 1)
+    out = torch.empty(N, H, W, C, dtype=torch.float16, device=cuda_device)
+    op = ops.ConvOp([(_nhwc_half(h, cuda_device), ops.MODE_3x3, aff.to(cuda_device), 0, 1),
+                     (_nhwc_half(x1, cuda_device), ops.MODE_1x1), (_nhwc_half(x2, cuda_device), ops.MODE_1x1)],
+                    wp.contiguous().to(cuda_device), out=out)
+    op.launch()
+    torch.cuda.synchronize()
+    _check(_from_nhwc(out), ref, 2.5e-3, "fused + raw shortcut")
+
+
+def test_fused_operand_planar_output(cuda_device):
+    """norm_out - swish - conv_out (ddpm/diffusion.py:575-578): fused operand, 64-wide padded N tile, fp32 planar store"""
+    ops = _ops()
+    g = torch.Generator().manual_seed(13)
+    N, H, W, C, Co = 2, 32, 32, 64, 3
+    x = _rand((N, C, H, W), g)
+    aff = torch.stack([_rand((N, C), g) * 0.5 + 1.0, _rand((N, C), g) * 0.5], dim=-1).contiguous()
+    w = torch.zeros(64, C, 3, 3)
+    w[:Co] = _rand((Co, C, 3, 3), g, 1.0 / math.sqrt(9 * C))
+    y = _h(x) * aff[..., 0].double()[:, :, None, None] + aff[..., 1].double()[:, :, None, None]
+    y = _h((y * torch.sigmoid(y)).float())
+    ref = F.conv2d(y, _h(w[:Co]), padding=1)
+    outp = torch.zeros(N, Co, H, W, dtype=torch.float32, device=cuda_device)
+    op = ops.ConvOp([(_nhwc_half(x, cuda_device), ops.MODE_3x3, aff.to(cuda_device), 0, 1)],
+                    ops.pack_conv_weight(w).to(cuda_device), out_shape=(N, H, W, 64), out_planar=outp)
+    op.launch()
+    torch.cuda.synchronize()
+    _check(outp.cpu(), ref, 2.5e-3, "fused planar")
