@@ -28,7 +28,8 @@ namespace asyrp {
 
 static constexpr int kMaxSeg = 3;
 static constexpr int kNumTransformWarps = 8;
-static constexpr int kNumThreads = 192 + 32 * kNumTransformWarps;  // + transform warps (6..13)
+static constexpr int kWarpB = 6 + kNumTransformWarps;                   // weight (B operand) producer warp
+static constexpr int kNumThreads = 32 * (kWarpB + 1);  // warps: 0 A-producer, 1 MMA, 2..5 epilogue, 6..13 transform, 14 B-producer
 
 struct ConvSegDev {
   int nchunks;  // C / 64
@@ -125,19 +126,19 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
   const int total_tiles = p.m_tiles * p.n_tiles;
 
   if (warp == 0) {
-    // ======================================================== TMA producer
+    // ======================================================== TMA producer, A operand (activations)
+    // A and B have independent rings and independent producer threads, so the activation prefetch (which the
+    // transform warps must also touch) runs a full A-ring ahead regardless of the weight ring's depth.
     if (lane == 0) {
-      int sa = 0, sb = 0;
-      uint32_t pa = 0, pb = 0;
+      int sa = 0;
+      uint32_t pa = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int mt = tile % p.m_tiles, nt = tile / p.m_tiles;
+        const int mt = tile % p.m_tiles;
         const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, tn = mt / (p.tiles_x * p.tiles_y);
         const int x0 = tx * p.TW, y0 = ty * THT, n0 = tn * p.NB;
-        const int bz = p.b_batched ? n0 : 0;
         for (int s = 0; s < p.nseg; ++s) {
           const ConvSegDev sg = p.seg[s];
           const int ncopies = (sg.mode == 0 || sg.mode == 3) ? 1 : (sg.mode == 1 ? 3 : 9);
-          const int ntaps = sg.mode == 1 ? 3 : (sg.mode == 3 ? 9 : 1);
           const uint32_t a_bytes = sg.mode == 3 ? (THT + 2) * (p.TW + 2) * 128u
                                                 : (sg.mode == 1 ? (THT + 2) : THT) * p.row_bytes;
           for (int ch = 0; ch < sg.nchunks; ++ch) {
@@ -157,6 +158,26 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
                             y0 + (ky >> 1));
               }
               if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == kWarpB) {
+    // ======================================================== TMA producer, B operand (weights)
+    if (lane == 0) {
+      int sb = 0;
+      uint32_t pb = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int mt = tile % p.m_tiles, nt = tile / p.m_tiles;
+        const int tn = mt / (p.tiles_x * p.tiles_y);
+        const int bz = p.b_batched ? tn * p.NB : 0;
+        for (int s = 0; s < p.nseg; ++s) {
+          const ConvSegDev sg = p.seg[s];
+          const int ncopies = (sg.mode == 0 || sg.mode == 3) ? 1 : (sg.mode == 1 ? 3 : 9);
+          const int ntaps = sg.mode == 1 ? 3 : (sg.mode == 3 ? 9 : 1);
+          for (int ch = 0; ch < sg.nchunks; ++ch) {
+            for (int cp = 0; cp < ncopies; ++cp) {
               for (int tp = 0; tp < ntaps; ++tp) {
                 // tap index in the weight matrix: ky*3+kx
                 const int tap = sg.mode == 0 ? 0 : (sg.mode == 1 ? tp * 3 + cp : (sg.mode == 3 ? tp : cp));
@@ -225,7 +246,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
     }
     __syncwarp();
   } else if (warp >= 6) {
-    // ======================================================== operand transform (warps 6..9), in place
+    // ======================================================== operand transform (warps 6..13), in place
     if (p.any_transform) {
       constexpr int kLanes = kNumTransformWarps * 4;  // pixels handled concurrently (8 threads per pixel)
       const int tt = threadIdx.x - 6 * 32;

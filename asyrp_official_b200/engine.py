@@ -42,10 +42,10 @@ class Act:
 
 
 class Launch:
-    __slots__ = ("fn", "kind", "flops", "nbytes")
+    __slots__ = ("fn", "kind", "flops", "nbytes", "desc")
 
     def __init__(self, fn, kind, flops, nbytes):
-        self.fn, self.kind, self.flops, self.nbytes = fn, kind, flops, nbytes
+        self.fn, self.kind, self.flops, self.nbytes, self.desc = fn, kind, flops, nbytes, kind
 
     def __call__(self):
         self.fn()
@@ -260,6 +260,8 @@ class Plan:
         nbytes = 2.0 * (sum(sg[0].t.numel() for sg in segs) + weight.numel() + self.N * H * W * Cout
                         + (residual.t.numel() if residual is not None else 0))
         self._emit(op.launch, "conv", flops, nbytes)
+        self._cur[-1].desc = " + ".join(f"{'1x1 3x3 s2'.split()[sg[1]]}{'*' if sg[2] is not None else ''}:{sg[0].C}"
+                                        for sg in segs) + f" -> {Cout} @{H}x{W}"
         return out, op
 
     # ------------------------------------------------------------------ blocks
