@@ -27,9 +27,12 @@
 namespace asyrp {
 
 static constexpr int kMaxSeg = 3;
+static constexpr int kNumEpilogueWarps = 8;   // two warps per TMEM lane quarter, alternating 32-column chunks
 static constexpr int kNumTransformWarps = 8;
-static constexpr int kWarpB = 6 + kNumTransformWarps;                   // weight (B operand) producer warp
-static constexpr int kNumThreads = 32 * (kWarpB + 1);  // warps: 0 A-producer, 1 MMA, 2..5 epilogue, 6..13 transform, 14 B-producer
+static constexpr int kWarpT = 2 + kNumEpilogueWarps;            // first transform warp
+static constexpr int kWarpB = kWarpT + kNumTransformWarps;      // weight (B operand) producer warp
+// warps: 0 A-producer, 1 MMA issuer, 2..9 epilogue, 10..17 operand transform, 18 B-producer
+static constexpr int kNumThreads = 32 * (kWarpB + 1);
 
 struct ConvSegDev {
   int nchunks;  // C / 64
@@ -106,7 +109,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 4);
+      mbar_init(&tempty[i], kNumEpilogueWarps);
     }
     fence_mbar_init();
   }
@@ -245,11 +248,11 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
       }
     }
     __syncwarp();
-  } else if (warp >= 6) {
-    // ======================================================== operand transform (warps 6..13), in place
+  } else if (warp >= kWarpT) {
+    // ======================================================== operand transform warps, in place
     if (p.any_transform) {
       constexpr int kLanes = kNumTransformWarps * 4;  // pixels handled concurrently (8 threads per pixel)
-      const int tt = threadIdx.x - 6 * 32;
+      const int tt = threadIdx.x - kWarpT * 32;
       const int jl = tt & 7;                  // logical 16B chunk = channels [jl*8, jl*8+8) of the 64-channel slab
       const int pl = tt >> 3;                 // pixel lane
       int sa = 0;
@@ -332,12 +335,15 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
       }
     }
   } else {
-    // ======================================================== epilogue (warps 2..5)
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // ======================================================== epilogue (warps 2..9)
+    // Warp (q, half): TMEM lanes [32q, 32q+32) = 32 pixels of every sub-tile, column chunks cc = half, half+2, ...
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;  // which alternate 32-column chunks this warp drains
     const int ep_tid = (warp - 2) * 32 + lane;
     const int row = q * 32 + lane;
     const int xx = row % p.TW, nn = (row / p.TW) % p.NB, yy = row / (p.TW * p.NB);
     const int tiles_per_sample = p.tiles_x * p.tiles_y;
+    constexpr int kEpThreads = kNumEpilogueWarps * 32;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -345,131 +351,141 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
       const int mt = tile % p.m_tiles, nt = tile / p.m_tiles;
       const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, tn = mt / tiles_per_sample;
       const int x = tx * p.TW + xx, n = tn * p.NB + nn;
+      const int tile_in_sample = ty * p.tiles_x + tx;
       float* st = s_stats + acc * (4 * BN);
-      float sacc[BN / 32];
-#pragma unroll
-      for (int i = 0; i < BN / 32; ++i) sacc[i] = 0.f;
 
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
 #pragma unroll 1
-      for (int sub = 0; sub < MT; ++sub) {
-      const int y = ty * THT + sub * p.TH + yy;
-      const bool valid = (x < p.W) && (y < p.H) && (n < p.N);
-      const size_t pix = (static_cast<size_t>(n) * p.H + y) * p.W + x;
-#pragma unroll
-      for (int cc = 0; cc < BN / 32; ++cc) {
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * (MT * BN) + sub * BN + cc * 32, r);
-        tmem_ld_wait();
+      for (int cc = half; cc < BN / 32; cc += 2) {
         const int c0 = nt * BN + cc * 32;
-        float v[32];
+        float ws[32];  // per-lane partial statistics of this chunk, summed over the sub-tiles
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-        if (p.ebias != nullptr) {
-          const float* eb = p.ebias + static_cast<size_t>(valid ? n : 0) * p.ebias_stride + c0;
+        for (int j = 0; j < 32; ++j) ws[j] = 0.f;
+#pragma unroll 1
+        for (int sub = 0; sub < MT; ++sub) {
+          const int y = ty * THT + sub * p.TH + yy;
+          const bool valid = (x < p.W) && (y < p.H) && (n < p.N);
+          const size_t pix = (static_cast<size_t>(n) * p.H + y) * p.W + x;
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * (MT * BN) + sub * BN + cc * 32, r);
+          tmem_ld_wait();
+          float v[32];
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float4 b4 = *reinterpret_cast<const float4*>(eb + i);
-            v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
-          }
-        }
-        if (p.acc_scale != 1.0f) {
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+          if (p.ebias != nullptr) {
+            const float* eb = p.ebias + static_cast<size_t>(valid ? n : 0) * p.ebias_stride + c0;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] *= p.acc_scale;
-        }
-        if (p.res != nullptr && valid) {
-          const uint4* rp = reinterpret_cast<const uint4*>(p.res + pix * p.Cout + c0);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint4 u = rp[j];
-            const __half2* h2 = reinterpret_cast<const __half2*>(&u);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const float2 f = __half22float2(h2[k]);
-              v[j * 8 + k * 2] += p.res_scale * f.x;
-              v[j * 8 + k * 2 + 1] += p.res_scale * f.y;
+            for (int i = 0; i < 32; i += 4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(eb + i);
+              v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
             }
           }
-        }
-        if (p.out_planar != nullptr) {
-          if (valid && c0 == 0) {
-            const size_t hw = static_cast<size_t>(p.H) * p.W;
-            float* pp = p.out_planar + static_cast<size_t>(n) * p.planar_c * hw + static_cast<size_t>(y) * p.W + x;
+          if (p.acc_scale != 1.0f) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-              if (i < p.planar_c) pp[i * hw] = v[i];
+            for (int i = 0; i < 32; ++i) v[i] *= p.acc_scale;
           }
-        } else if (valid) {
-          uint4* op = reinterpret_cast<uint4*>(p.out + pix * p.Cout + c0);
+          if (p.res != nullptr && valid) {
+            const uint4* rp = reinterpret_cast<const uint4*>(p.res + pix * p.Cout + c0);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint4 u;
-            __half2* h2 = reinterpret_cast<__half2*>(&u);
+            for (int j = 0; j < 4; ++j) {
+              const uint4 u = rp[j];
+              const __half2* h2 = reinterpret_cast<const __half2*>(&u);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) h2[k] = __floats2half2_rn(v[j * 8 + k * 2], v[j * 8 + k * 2 + 1]);
-            op[j] = u;
-          }
-        }
-        if (p.stats != nullptr) {
-          // per-sample partial sums over this warp's 32 pixels, at channel-pair granularity:
-          // slot j<16 : sum of pair j ; slot j>=16 : sum of squares of pair j-16
-          for (int sn = 0; sn < p.NB; ++sn) {
-            const bool mine = valid && (nn == sn);
-            float w[32];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float a = mine ? v[2 * j] : 0.f, b = mine ? v[2 * j + 1] : 0.f;
-              w[j] = a + b;
-              w[16 + j] = a * a + b * b;
-            }
-            // recursive-halving reduce-scatter: after the loop w[0] on lane L is the warp total of slot L
-#pragma unroll
-            for (int h = 16; h >= 1; h >>= 1) {
-              const bool up = (lane & h) != 0;
-#pragma unroll
-              for (int i = 0; i < h; ++i) {
-                const float send = up ? w[i] : w[i + h];
-                const float keep = up ? w[i + h] : w[i];
-                w[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+              for (int k = 0; k < 4; ++k) {
+                const float2 f = __half22float2(h2[k]);
+                v[j * 8 + k * 2] += p.res_scale * f.x;
+                v[j * 8 + k * 2 + 1] += p.res_scale * f.y;
               }
             }
-            // s_stats[acc][sn?]: NB>1 tiles are tiny layers; fold sn into the slot by direct global write
+          }
+          if (p.out_planar != nullptr) {
+            if (valid && c0 == 0) {
+              const size_t hw = static_cast<size_t>(p.H) * p.W;
+              float* pp = p.out_planar + static_cast<size_t>(n) * p.planar_c * hw + static_cast<size_t>(y) * p.W + x;
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                if (i < p.planar_c) pp[i * hw] = v[i];
+            }
+          } else if (valid) {
+            uint4* op = reinterpret_cast<uint4*>(p.out + pix * p.Cout + c0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 u;
+              __half2* h2 = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) h2[k] = __floats2half2_rn(v[j * 8 + k * 2], v[j * 8 + k * 2 + 1]);
+              op[j] = u;
+            }
+          }
+          if (p.stats != nullptr) {
             if (p.NB == 1) {
-              sacc[cc] += w[0];
+              // slot j<16 : sum of channel pair j ; slot j>=16 : sum of squares of pair j-16 (this lane's pixel)
+              if (valid) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  ws[j] += v[2 * j] + v[2 * j + 1];
+                  ws[16 + j] += v[2 * j] * v[2 * j] + v[2 * j + 1] * v[2 * j + 1];
+                }
+              }
             } else {
-              // one atomic per (warp, sample, slot): few tiles, low contention, fp32 order-dependent only
-              // across the 4 warps of a tile -> made deterministic by writing per-warp slots
-              const int ns = tn * p.NB + sn;
-              if (ns < p.N) {
-                const int tile_in_sample = ty * p.tiles_x + tx;
-                float* g = p.stats + (((static_cast<size_t>(ns) * tiles_per_sample + tile_in_sample) * 4 + q) *
-                                          (p.Cout / 2) + (c0 / 2) + (lane & 15)) * 2 + (lane >> 4);
-                *g = w[0];
+              // tiles spanning several samples (tiny layers): one masked warp reduction per sample
+              for (int sn = 0; sn < p.NB; ++sn) {
+                const bool mine = valid && (nn == sn);
+                float w[32];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  const float a = mine ? v[2 * j] : 0.f, b = mine ? v[2 * j + 1] : 0.f;
+                  w[j] = a + b;
+                  w[16 + j] = a * a + b * b;
+                }
+#pragma unroll
+                for (int h = 16; h >= 1; h >>= 1) {
+                  const bool up = (lane & h) != 0;
+#pragma unroll
+                  for (int i = 0; i < h; ++i) {
+                    const float send = up ? w[i] : w[i + h];
+                    const float keep = up ? w[i + h] : w[i];
+                    w[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+                  }
+                }
+                const int ns = tn * p.NB + sn;
+                if (ns < p.N) {  // one slot per (sample, tile, lane quarter): deterministic, no atomics
+                  float* g = p.stats + (((static_cast<size_t>(ns) * tiles_per_sample + tile_in_sample) * 4 + q) *
+                                            (p.Cout / 2) + (c0 / 2) + (lane & 15)) * 2 + (lane >> 4);
+                  *g = w[0];
+                }
               }
             }
           }
-        }
-      }
-      }  // sub
-      if (p.stats != nullptr && p.NB == 1) {
+        }  // sub
+        if (p.stats != nullptr && p.NB == 1) {
+          // recursive-halving reduce-scatter over the 32 lanes: afterwards ws[0] on lane L is the total of slot L
 #pragma unroll
-        for (int cc = 0; cc < BN / 32; ++cc) st[(q * (BN / 32) + cc) * 32 + lane] = sacc[cc];
-      }
+          for (int h = 16; h >= 1; h >>= 1) {
+            const bool up = (lane & h) != 0;
+#pragma unroll
+            for (int i = 0; i < h; ++i) {
+              const float send = up ? ws[i] : ws[i + h];
+              const float keep = up ? ws[i + h] : ws[i];
+              ws[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+            }
+          }
+          st[(q * (BN / 32) + cc) * 32 + lane] = ws[0];
+        }
+      }  // cc
       // accumulator fully drained into registers/global: release it to the MMA warp
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
 
       if (p.stats != nullptr && p.NB == 1) {
-        named_bar_sync(1, 128);
-        // 128 threads: one (chunk, slot) each for BN=128; loop for other BN
-        for (int e = ep_tid; e < BN; e += 128) {
+        named_bar_sync(1, kEpThreads);
+        for (int e = ep_tid; e < BN; e += kEpThreads) {
           const int cc = e >> 5, j = e & 31;
           float tot = 0.f;
 #pragma unroll
           for (int qq = 0; qq < 4; ++qq) tot += st[(qq * (BN / 32) + cc) * 32 + j];
-          const int tile_in_sample = ty * p.tiles_x + tx;
           float* g = p.stats + ((static_cast<size_t>(tn) * tiles_per_sample + tile_in_sample) * (p.Cout / 2) +
                                 (nt * BN + cc * 32) / 2 + (j & 15)) * 2 + (j >> 4);
           *g = tot;
