@@ -71,7 +71,11 @@ struct ConvParams {
   int any_transform;       // some segment has an affine: the MMA warp then waits on readyA instead of fullA
 };
 
-template <int BN, int MT>
+// SWAP: operand roles exchanged — the weight tile (128 output channels) is the M side and the MT*128 pixels are the
+// N side of ONE N=256 MMA per K step, so D is [channel lane][pixel column].  Per MMA the tensor core then reads
+// 4 KB (weights) + 8 KB (pixels) of shared memory per 128 cycles instead of 4 + 4 KB per 64 cycles: the Cout=128
+// layers (70% of the FLOPs) stop being shared-memory-bandwidth bound.
+template <int BN, int MT, bool SWAP = false>
 __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B operands need 1024B alignment
@@ -80,7 +84,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   constexpr uint32_t kBStage = BN * 128;
-  constexpr uint32_t kTmemCols = 2 * MT * BN;  // two accumulator sets (epilogue / MMA overlap)
+  static_assert(!SWAP || (BN == 128 && MT == 2), "swapped-operand variant: 128 channels x 256 pixels");
+  constexpr uint32_t kAccCols = SWAP ? MT * 128 : MT * BN;  // fp32 columns of one accumulator set
+  constexpr uint32_t kTmemCols = 2 * kAccCols;                // two sets (epilogue / MMA overlap)
   static_assert(kTmemCols <= 512 && kTmemCols >= 32, "TMEM budget");
 
   uint8_t* sA = smem;
@@ -197,7 +203,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
   } else if (warp == 1) {
     // ======================================================== MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_f16_m128(BN);
+      constexpr uint32_t idesc = umma_idesc_f16_m128(SWAP ? MT * 128 : BN);
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       int it = 0;
@@ -206,7 +212,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * (MT * BN);
+        const uint32_t d_tmem = tmem_base + acc * kAccCols;
         uint32_t accumulate = 0;
         for (int s = 0; s < p.nseg; ++s) {
           const ConvSegDev sg = p.seg[s];
@@ -227,13 +233,21 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
                 const uint32_t b_addr = smem_u32(sB + sb * kBStage);
                 // mode 1: dy tap = row shift inside the dx copy; mode 3: (ky, kx) = pixel offset inside the halo tile
                 const uint32_t tap_off = sg.mode == 3 ? (tp / 3) * halo_pitch + (tp % 3) * 128u : tp * p.row_bytes;
-#pragma unroll
-                for (int sub = 0; sub < MT; ++sub) {
-                  const uint32_t a_addr = a_base + sub * sub_stride + tap_off;
+                if constexpr (SWAP) {
+                  // M = 128 weight rows, N = all MT*128 pixel rows (uniform 8-row-group pitch across sub-tiles)
 #pragma unroll
                   for (int k = 0; k < 4; ++k)
-                    umma_f16(d_tmem + sub * BN, umma_desc_k128(a_addr + k * 32, sbo), umma_desc_k128(b_addr + k * 32),
+                    umma_f16(d_tmem, umma_desc_k128(b_addr + k * 32), umma_desc_k128(a_base + tap_off + k * 32, sbo),
                              idesc, (accumulate | k) ? 1u : 0u);
+                } else {
+#pragma unroll
+                  for (int sub = 0; sub < MT; ++sub) {
+                    const uint32_t a_addr = a_base + sub * sub_stride + tap_off;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                      umma_f16(d_tmem + sub * BN, umma_desc_k128(a_addr + k * 32, sbo),
+                               umma_desc_k128(b_addr + k * 32), idesc, (accumulate | k) ? 1u : 0u);
+                  }
                 }
                 accumulate = 1;
                 umma_commit(&emptyB[sb]);
@@ -356,6 +370,41 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
 
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
+      if constexpr (SWAP) {
+        // thread = output channel (TMEM lane), registers = 32 consecutive pixels of the 8(16)-wide x 32-tall tile
+        const int c = nt * 128 + q * 32 + lane;
+        const float eb = p.ebias != nullptr ? p.ebias[static_cast<size_t>(tn) * p.ebias_stride + c] : 0.f;
+        float s1 = 0.f, s2 = 0.f;
+        const int tws = 31 - __clz(p.TW);  // TW is 8 or 16
+#pragma unroll 1
+        for (int cc = half; cc < (MT * 128) / 32; cc += 2) {
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kAccCols + cc * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int m = cc * 32 + i;
+            const int px = tx * p.TW + (m & (p.TW - 1)), py = ty * THT + (m >> tws);
+            if (px < p.W && py < p.H) {
+              const size_t o = ((static_cast<size_t>(tn) * p.H + py) * p.W + px) * p.Cout + c;
+              float v = (__uint_as_float(r[i]) + eb) * p.acc_scale;
+              if (p.res != nullptr) v += p.res_scale * __half2float(p.res[o]);
+              p.out[o] = __float2half_rn(v);
+              s1 += v;
+              s2 += v * v;
+            }
+          }
+        }
+        if (p.stats != nullptr) {
+          // channel pair = lanes (2j, 2j+1); each (tile, half) owns one slot: nothing to reduce across warps
+          s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+          s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
+          if ((lane & 1) == 0)
+            *reinterpret_cast<float2*>(p.stats + ((static_cast<size_t>(tn) * tiles_per_sample * 2 +
+                                                    tile_in_sample * 2 + half) * (p.Cout / 2) + (c >> 1)) * 2) =
+                make_float2(s1, s2);
+        }
+      } else {
 #pragma unroll 1
       for (int cc = half; cc < BN / 32; cc += 2) {
         const int c0 = nt * BN + cc * 32;
@@ -474,12 +523,13 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
           st[(q * (BN / 32) + cc) * 32 + lane] = ws[0];
         }
       }  // cc
+      }  // !SWAP
       // accumulator fully drained into registers/global: release it to the MMA warp
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
 
-      if (p.stats != nullptr && p.NB == 1) {
+      if (!SWAP && p.stats != nullptr && p.NB == 1) {
         named_bar_sync(1, kEpThreads);
         for (int e = ep_tid; e < BN; e += kEpThreads) {
           const int cc = e >> 5, j = e & 31;
@@ -518,7 +568,7 @@ using namespace asyrp;
 
 static const void* conv_kernel_ptr(int BN, int MT) {
   if (BN == 256) return reinterpret_cast<const void*>(&conv_gemm_kernel<256, 1>);
-  if (BN == 128) return MT == 2 ? reinterpret_cast<const void*>(&conv_gemm_kernel<128, 2>)
+  if (BN == 128) return MT == 2 ? reinterpret_cast<const void*>(&conv_gemm_kernel<128, 2, true>)
                                 : reinterpret_cast<const void*>(&conv_gemm_kernel<128, 1>);
   return MT == 2 ? reinterpret_cast<const void*>(&conv_gemm_kernel<64, 2>)
                  : reinterpret_cast<const void*>(&conv_gemm_kernel<64, 1>);
@@ -597,8 +647,10 @@ ASYRP_API int asyrp_conv_stats_tiles(int H, int W, int Cout, int has_3x3) {
   int TW, TH, NB;
   const int halo = has_3x3 && conv_halo_ok(H, W);
   conv_tile_shape(H, W, halo, &TW, &TH, &NB);
-  const int tht = TH * conv_mt(H, W, Cout, halo);
+  const int mt = conv_mt(H, W, Cout, halo);
+  const int tht = TH * mt;
   const int tiles = ((W + TW - 1) / TW) * ((H + tht - 1) / tht);
+  if (conv_bn(Cout) == 128 && mt == 2) return tiles * 2;  // swapped-operand kernel: one slot per (tile, warp half)
   return NB == 1 ? tiles : tiles * 4;
 }
 
@@ -689,6 +741,8 @@ ASYRP_API int asyrp_conv_create(const AsyrpConvDesc* d, void** out_op) {
   p.planar_c = d->planar_c;
   ASYRP_REQUIRE(d->out_planar == nullptr || (d->planar_c >= 1 && d->planar_c <= 8),
                 "asyrp_conv_create: planar_c=%d out of range", d->planar_c);
+  ASYRP_REQUIRE(!(d->out_planar != nullptr && op->BN == 128 && op->MT == 2),
+                "asyrp_conv_create: planar output needs Cout == 64 (padded conv_out)");
   p.res = static_cast<const __half*>(d->residual);
   p.res_scale = d->res_scale;
   p.acc_scale = d->acc_scale;
