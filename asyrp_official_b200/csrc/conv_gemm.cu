@@ -376,23 +376,49 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
         const float eb = p.ebias != nullptr ? p.ebias[static_cast<size_t>(tn) * p.ebias_stride + c] : 0.f;
         float s1 = 0.f, s2 = 0.f;
         const int tws = 31 - __clz(p.TW);  // TW is 8 or 16
+        const size_t row_stride = static_cast<size_t>(p.W) * p.Cout;
+        const __half* __restrict__ resp = p.res;
+        __half* __restrict__ outp = p.out;
+        const bool odd = (lane & 1) != 0;
 #pragma unroll 1
         for (int cc = half; cc < (MT * 128) / 32; cc += 2) {
           uint32_t r[32];
           tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kAccCols + cc * 32, r);
+          // element offset of the chunk's first pixel (32 pixels = 32/TW image rows of the tile)
+          const int py0 = ty * THT + ((cc * 32) >> tws), px0 = tx * p.TW;
+          const size_t o0 = ((static_cast<size_t>(tn) * p.H + py0) * p.W + px0) * p.Cout + c;
+          float rv[32];
+          if (resp != nullptr) {  // all residual loads first: independent of the stores below
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int dy = i >> tws, dx = i & (p.TW - 1);
+              rv[i] = (px0 + dx < p.W && py0 + dy < p.H) ? __half2float(resp[o0 + dy * row_stride + dx * p.Cout]) : 0.f;
+            }
+          }
           tmem_ld_wait();
+          float v[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            const int m = cc * 32 + i;
-            const int px = tx * p.TW + (m & (p.TW - 1)), py = ty * THT + (m >> tws);
-            if (px < p.W && py < p.H) {
-              const size_t o = ((static_cast<size_t>(tn) * p.H + py) * p.W + px) * p.Cout + c;
-              float v = (__uint_as_float(r[i]) + eb) * p.acc_scale;
-              if (p.res != nullptr) v += p.res_scale * __half2float(p.res[o]);
-              p.out[o] = __float2half_rn(v);
-              s1 += v;
-              s2 += v * v;
+            v[i] = (__uint_as_float(r[i]) + eb) * p.acc_scale;
+            if (resp != nullptr) v[i] += p.res_scale * rv[i];
+          }
+          // lanes (2j, 2j+1) hold adjacent channels: exchange so that the even lane stores pixel i and the odd lane
+          // pixel i+1, each as one half2 (4 B) -> a warp store covers two pixels x 64 B
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float mine = odd ? v[i + 1] : v[i];
+            const float give = odd ? v[i] : v[i + 1];
+            const float got = __shfl_xor_sync(0xffffffffu, give, 1);
+            const int ii = odd ? i + 1 : i;
+            const int dy = ii >> tws, dx = ii & (p.TW - 1);
+            const bool ok0 = (px0 + (i & (p.TW - 1)) < p.W) && (py0 + (i >> tws) < p.H);
+            const bool ok1 = (px0 + ((i + 1) & (p.TW - 1)) < p.W) && (py0 + ((i + 1) >> tws) < p.H);
+            if (odd ? ok1 : ok0) {
+              const __half2 h2 = odd ? __floats2half2_rn(got, mine) : __floats2half2_rn(mine, got);
+              *reinterpret_cast<__half2*>(outp + (o0 - (odd ? 1 : 0)) + dy * row_stride + dx * p.Cout) = h2;
             }
+            if (ok0) { s1 += v[i]; s2 += v[i] * v[i]; }
+            if (ok1) { s1 += v[i + 1]; s2 += v[i + 1] * v[i + 1]; }
           }
         }
         if (p.stats != nullptr) {
