@@ -628,20 +628,32 @@ struct AsyrpConvDesc {
   int planar_c;
 };
 
-static int conv_bn(int Cout) { return (Cout % 256 == 0) ? 256 : (Cout % 128 == 0 ? 128 : 64); }
-
 static void conv_tile_shape(int H, int W, int halo, int* TW, int* TH, int* NB);
 
 // A 3x3/s1 conv whose output is at least 8 wide and 16 tall uses 8x16-pixel sub-tiles fed from one halo tile per
 // 64-channel chunk ("halo" geometry, segment mode 3); otherwise three dx-shifted copies (mode 1).
 static int conv_halo_ok(int H, int W) { return H % 16 == 0 && W % 8 == 0; }
 
-// CTA tile = MT sub-tiles of 128 pixels stacked in y.  Two sub-tiles halve the weight (B operand) traffic per
-// FLOP; TMEM holds 2*MT*BN fp32 columns (<= 512), so MT = 2 needs BN <= 128.
-static int conv_mt(int H, int W, int Cout, int halo) {
+// Tile configuration: BN output channels x MT sub-tiles of 128 pixels per CTA tile.  Larger tiles re-use operands
+// better (BN=256, or the swapped-operand 128x256 variant for BN=128/MT=2: TMEM holds 2*MT*BN <= 512 fp32 columns);
+// small layers instead need enough tiles to occupy the 148 SMs.  Pick the most efficient configuration that still
+// yields ~a full wave of tiles, else the one with the most tiles.
+static void conv_config(int N, int H, int W, int Cout, int halo, int* BN, int* MT) {
   int TW, TH, NB;
   conv_tile_shape(H, W, halo, &TW, &TH, &NB);
-  return (conv_bn(Cout) <= 128 && NB == 1 && H > 1 && H % (2 * TH) == 0) ? 2 : 1;
+  const int tiles_x = (W + TW - 1) / TW, tiles_n = (N + NB - 1) / NB;
+  const int cand[5][2] = {{256, 1}, {128, 2}, {128, 1}, {64, 2}, {64, 1}};  // by decreasing operand re-use
+  int best = -1, best_tiles = -1;
+  for (int i = 0; i < 5; ++i) {
+    const int bn = cand[i][0], mt = cand[i][1];
+    if (Cout % bn != 0) continue;
+    if (mt == 2 && !(NB == 1 && H > 1 && H % (2 * TH) == 0)) continue;
+    const int tiles = tiles_x * ((H + TH * mt - 1) / (TH * mt)) * tiles_n * (Cout / bn);
+    if (tiles >= 120) { best = i; break; }
+    if (tiles > best_tiles) { best = i; best_tiles = tiles; }
+  }
+  *BN = cand[best][0];
+  *MT = cand[best][1];
 }
 
 static void conv_tile_shape(int H, int W, int halo, int* TW, int* TH, int* NB) {
@@ -668,15 +680,15 @@ static void conv_tile_shape(int H, int W, int halo, int* TW, int* TH, int* NB) {
 
 // number of pixel tiles per sample the stats buffer must hold: stats is [N][tiles][Cout/2][2] floats.
 // For layers whose tile spans several samples (NB>1) the kernel writes one slot per epilogue warp (4).
-// `halo`: the conv producing the statistics contains a 3x3 stride-1 segment (tile geometry depends on it)
-ASYRP_API int asyrp_conv_stats_tiles(int H, int W, int Cout, int has_3x3) {
-  int TW, TH, NB;
+// has_3x3: the conv producing the statistics contains a 3x3 stride-1 segment (tile geometry depends on it)
+ASYRP_API int asyrp_conv_stats_tiles(int N, int H, int W, int Cout, int has_3x3) {
+  int TW, TH, NB, bn, mt;
   const int halo = has_3x3 && conv_halo_ok(H, W);
   conv_tile_shape(H, W, halo, &TW, &TH, &NB);
-  const int mt = conv_mt(H, W, Cout, halo);
+  conv_config(N, H, W, Cout, halo, &bn, &mt);
   const int tht = TH * mt;
   const int tiles = ((W + TW - 1) / TW) * ((H + tht - 1) / tht);
-  if (conv_bn(Cout) == 128 && mt == 2) return tiles * 2;  // swapped-operand kernel: one slot per (tile, warp half)
+  if (bn == 128 && mt == 2) return tiles * 2;  // swapped-operand kernel: one slot per (tile, warp half)
   return NB == 1 ? tiles : tiles * 4;
 }
 
@@ -695,13 +707,13 @@ ASYRP_API int asyrp_conv_create(const AsyrpConvDesc* d, void** out_op) {
   ASYRP_REQUIRE(p.TW * p.TH * p.NB == 128, "asyrp_conv_create: cannot tile H=%d W=%d into 128 pixels", d->H,
                 d->W);
   ASYRP_REQUIRE(!(d->weight_batched && p.NB != 1), "asyrp_conv_create: batched weights need NB==1");
-  op->MT = p.MT = conv_mt(d->H, d->W, d->Cout, halo);
+  conv_config(d->N, d->H, d->W, d->Cout, halo, &op->BN, &op->MT);
+  p.MT = op->MT;
   const int THT = p.TH * p.MT;
   p.tiles_x = (d->W + p.TW - 1) / p.TW;
   p.tiles_y = (d->H + THT - 1) / THT;
   p.tiles_n = (d->N + p.NB - 1) / p.NB;
   p.m_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
-  op->BN = conv_bn(d->Cout);
   p.n_tiles = d->Cout / op->BN;
   p.row_bytes = p.NB * p.TW * 128;
   p.nseg = d->nseg;

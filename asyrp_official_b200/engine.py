@@ -42,10 +42,10 @@ class Act:
 
 
 class Launch:
-    __slots__ = ("fn", "kind", "flops", "nbytes", "desc")
+    __slots__ = ("fn", "kind", "flops", "nbytes", "desc", "has_res")
 
     def __init__(self, fn, kind, flops, nbytes):
-        self.fn, self.kind, self.flops, self.nbytes, self.desc = fn, kind, flops, nbytes, kind
+        self.fn, self.kind, self.flops, self.nbytes, self.desc, self.has_res = fn, kind, flops, nbytes, kind, False
 
     def __call__(self):
         self.fn()
@@ -131,6 +131,10 @@ def pack_weights(arch: Arch, sd, device, n_delta):
             # 1x1 shortcut on the raw (possibly concatenated) input: extra K columns of the same GEMM
             w2 = torch.cat([w2, ops.pack_conv_weight(sd[p + sc + ".weight"].detach().float())], dim=1)
             b2 = b2 + sd[p + sc + ".bias"].detach().float().cpu()
+        else:
+            # identity skip: x + h as K columns with an identity weight block (exact: fp16 x times 1.0 into the fp32
+            # accumulator) — the residual rides the TMA/tensor-core pipeline instead of scattered epilogue loads
+            w2 = torch.cat([w2, torch.eye(layer.cout, dtype=torch.float16)], dim=1)
         W[p + ".w2"], W[p + ".b2"] = w2.contiguous().to(device), f32(b2)
 
     def attn(layer):
@@ -214,7 +218,7 @@ class Plan:
         t = self.pool.alloc((self.N, H, W, C), torch.float16)
         st = None
         if stats:
-            st = self.pool.alloc((self.N, ops.conv_stats_tiles(H, W, C, has_3x3), C // 2, 2), torch.float32)
+            st = self.pool.alloc((self.N, ops.conv_stats_tiles(self.N, H, W, C, has_3x3), C // 2, 2), torch.float32)
         return Act(t, st)
 
     def _free(self, act):
@@ -262,6 +266,7 @@ class Plan:
         self._emit(op.launch, "conv", flops, nbytes)
         self._cur[-1].desc = " + ".join(f"{'1x1 3x3 s2'.split()[sg[1]]}{'*' if sg[2] is not None else ''}:{sg[0].C}"
                                         for sg in segs) + f" -> {Cout} @{H}x{W}"
+        self._cur[-1].has_res = residual is not None
         return out, op
 
     # ------------------------------------------------------------------ blocks
@@ -309,7 +314,8 @@ class Plan:
                                 ebias=W[p + ".b2"])
         else:
             resid = xr if xr is not None else srcs[0]
-            out, _ = self._conv(segs2, W[p + ".w2"], layer.cout, H, Wd, ebias=W[p + ".b2"], residual=resid)
+            out, _ = self._conv(segs2 + [(resid, MODE_1x1)], W[p + ".w2"], layer.cout, H, Wd, ebias=W[p + ".b2"],
+                                algo_flops=2.0 * self.N * H * Wd * layer.cout * 9 * layer.cout)
         self.pool.release(aff2)
         self._free(h)
         if xr is not None:

@@ -19,3 +19,7 @@ tot = sum(e[1] for e in agg.values())
 for d, (n, ms, fl) in sorted(agg.items(), key=lambda x: -x[1][1]):
     print(f"{d:70s} x{n:3d} {ms:8.3f} ms {ms/tot*100:5.1f}%  {fl/ms/1e9:7.1f} TF/s")
 print("conv total ms", tot)
+print("--- individual launches of 128->128 @256x256 single-segment fused convs")
+for L, (kind, ms, fl, nb) in zip(seq, prof):
+    if kind == "conv" and getattr(L, "desc", "") in ("3x3*:128 -> 128 @256x256", "3x3*:128 -> 128 @128x128", "3x3:128 -> 128 @256x256"):
+        print(L.desc, f"{ms*1000:.1f} us", f"{fl/ms/1e9:.0f} TF/s", "has_res" if getattr(L, "has_res", None) else "")
