@@ -134,7 +134,7 @@ def pack_weights(arch: Arch, sd, device, n_delta):
         else:
             # identity skip: x + h as K columns with an identity weight block (exact: fp16 x times 1.0 into the fp32
             # accumulator) — the residual rides the TMA/tensor-core pipeline instead of scattered epilogue loads
-            w2 = torch.cat([w2, torch.eye(layer.cout, dtype=torch.float16)], dim=1)
+            w2 = torch.cat([w2, torch.eye(layer.cout, dtype=w2.dtype, device=w2.device)], dim=1)
         W[p + ".w2"], W[p + ".b2"] = w2.contiguous().to(device), f32(b2)
 
     def attn(layer):

@@ -155,3 +155,32 @@ def test_runner_host_logic():
     with pytest.raises(ValueError):
         Asyrp(argparse.Namespace(user_defined_t_edit=None, user_defined_t_addnoise=None), load_config("celeba"),
               device="cpu").set_t_edit_t_addnoise()
+
+
+def test_weight_packing_layout():
+    """pack_weights is pure tensor reshuffling: check the K layouts the kernels rely on, on the CPU"""
+    from asyrp_official_b200 import arch, modules, synthetic
+    from asyrp_official_b200.engine import pack_weights
+    from oracle import adm as oa, ddpm as od
+    for a, make in ((arch.ddpm_arch(**od.MINI_CFG), None), (arch.adm_arch(**oa.MINI_HP), None)):
+        shapes = arch.param_shapes(a, 1)
+        from oracle import synth
+        sd = synth.synth_state_dict(shapes, 1234, "jittered")
+        W, emb_off, emb_total = pack_weights(a, sd, "cpu", 1)
+        assert emb_total == W["emb_cat.w"].shape[0] == W["emb_cat.b"].shape[0] and emb_total % 64 == 0
+        for stage in a.enc + [a.mid] + a.dec:
+            for layer in stage:
+                if isinstance(layer, arch.Res):
+                    p = layer.name
+                    assert W[p + ".w1"].shape == (layer.cout, 9 * layer.cin) and W[p + ".w1"].dtype == torch.float16
+                    # conv2: 9*cout columns, then the 1x1 shortcut (cin columns) or the identity skip (cout columns)
+                    assert W[p + ".w2"].shape == (layer.cout, 9 * layer.cout + layer.cin)
+                    if layer.cin == layer.cout:
+                        assert torch.equal(W[p + ".w2"][:, 9 * layer.cout:].float(), torch.eye(layer.cout))
+                    if layer.split:  # decoder: segment-major K (h columns of every tap, then skip columns of every tap)
+                        c0 = layer.split[0]
+                        key = p + (".conv1.weight" if a.family == "ddpm" else ".in_layers.2.weight")
+                        w = sd[key]
+                        assert torch.equal(W[p + ".w1"][:, :9 * c0].float().reshape(layer.cout, 3, 3, c0),
+                                           w[:, :c0].permute(0, 2, 3, 1).to(torch.float16).float())
+        assert W["conv_in.w"].shape[1] == 9 * 64 and W["conv_out.w"].shape[0] == 64
