@@ -38,7 +38,7 @@ class AsyrpConvDesc(C.Structure):
 # name -> (restype, argtypes); every symbol include/asyrp_b200.h declares
 SIGNATURES = {
     "asyrp_last_error": (C.c_char_p, []),
-    "asyrp_conv_stats_tiles": (c_int, [c_int, c_int, c_int, c_int, c_int]),
+    "asyrp_conv_stats_tiles": (c_int, [c_int, c_int, c_int, c_int]),
     "asyrp_conv_create": (c_int, [C.POINTER(AsyrpConvDesc), C.POINTER(c_void_p)]),
     "asyrp_conv_launch": (c_int, [c_void_p, c_void_p]),
     "asyrp_conv_set_scales": (c_int, [c_void_p, c_float, c_float]),

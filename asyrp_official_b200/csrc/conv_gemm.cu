@@ -637,11 +637,14 @@ static int conv_halo_ok(int H, int W) { return H % 16 == 0 && W % 8 == 0; }
 // Tile configuration: BN output channels x MT sub-tiles of 128 pixels per CTA tile.  Larger tiles re-use operands
 // better (BN=256, or the swapped-operand 128x256 variant for BN=128/MT=2: TMEM holds 2*MT*BN <= 512 fp32 columns);
 // small layers instead need enough tiles to occupy the 148 SMs.  Pick the most efficient configuration that still
-// yields ~a full wave of tiles, else the one with the most tiles.
-static void conv_config(int N, int H, int W, int Cout, int halo, int* BN, int* MT) {
+// yields ~a full wave of tiles at a NOMINAL batch of 8, else the one with the most tiles.  The choice must not
+// depend on the actual batch: the tile partition fixes the summation order of the GroupNorm partial sums, and a
+// sample's result has to be bit-identical whatever batch (or batch shard on another GPU) it is part of.
+static void conv_config(int H, int W, int Cout, int halo, int* BN, int* MT) {
   int TW, TH, NB;
   conv_tile_shape(H, W, halo, &TW, &TH, &NB);
-  const int tiles_x = (W + TW - 1) / TW, tiles_n = (N + NB - 1) / NB;
+  constexpr int kNominalBatch = 8;
+  const int tiles_x = (W + TW - 1) / TW, tiles_n = (kNominalBatch + NB - 1) / NB;
   const int cand[5][2] = {{256, 1}, {128, 2}, {128, 1}, {64, 2}, {64, 1}};  // by decreasing operand re-use
   int best = -1, best_tiles = -1;
   for (int i = 0; i < 5; ++i) {
@@ -681,11 +684,11 @@ static void conv_tile_shape(int H, int W, int halo, int* TW, int* TH, int* NB) {
 // number of pixel tiles per sample the stats buffer must hold: stats is [N][tiles][Cout/2][2] floats.
 // For layers whose tile spans several samples (NB>1) the kernel writes one slot per epilogue warp (4).
 // has_3x3: the conv producing the statistics contains a 3x3 stride-1 segment (tile geometry depends on it)
-ASYRP_API int asyrp_conv_stats_tiles(int N, int H, int W, int Cout, int has_3x3) {
+ASYRP_API int asyrp_conv_stats_tiles(int H, int W, int Cout, int has_3x3) {
   int TW, TH, NB, bn, mt;
   const int halo = has_3x3 && conv_halo_ok(H, W);
   conv_tile_shape(H, W, halo, &TW, &TH, &NB);
-  conv_config(N, H, W, Cout, halo, &bn, &mt);
+  conv_config(H, W, Cout, halo, &bn, &mt);
   const int tht = TH * mt;
   const int tiles = ((W + TW - 1) / TW) * ((H + tht - 1) / tht);
   if (bn == 128 && mt == 2) return tiles * 2;  // swapped-operand kernel: one slot per (tile, warp half)
@@ -707,7 +710,7 @@ ASYRP_API int asyrp_conv_create(const AsyrpConvDesc* d, void** out_op) {
   ASYRP_REQUIRE(p.TW * p.TH * p.NB == 128, "asyrp_conv_create: cannot tile H=%d W=%d into 128 pixels", d->H,
                 d->W);
   ASYRP_REQUIRE(!(d->weight_batched && p.NB != 1), "asyrp_conv_create: batched weights need NB==1");
-  conv_config(d->N, d->H, d->W, d->Cout, halo, &op->BN, &op->MT);
+  conv_config(d->H, d->W, d->Cout, halo, &op->BN, &op->MT);
   p.MT = op->MT;
   const int THT = p.TH * p.MT;
   p.tiles_x = (d->W + p.TW - 1) / p.TW;
@@ -766,13 +769,15 @@ ASYRP_API int asyrp_conv_create(const AsyrpConvDesc* d, void** out_op) {
   p.b_batched = d->weight_batched;
   p.a_stage_bytes = halo ? (((THT + 2) * (p.TW + 2) * 128u + 1023u) / 1024u) * 1024u
                          : (any3 ? THT + 2 : THT) * p.row_bytes;
-  // shared memory budget: ~205 KB of operand rings
   const uint32_t b_stage = op->BN * 128;
+  // operand rings: ~200 KB of shared memory.  Activations: 3-4 stages; weights: as deep as fits (<= 16 stages) —
+  // small-N tiles issue an MMA group every ~100 cycles, so the weight prefetch must run many K steps ahead of the
+  // ~1 us TMA latency.
   p.a_stages = (p.MT == 2 || halo) ? 3 : 4;
-  p.b_stages = op->BN == 256 ? 4 : 6;
-  if (halo && op->BN == 128) p.b_stages = 4;
-  while (p.a_stages * p.a_stage_bytes + p.b_stages * b_stage > 210 * 1024 && p.a_stages > 2) --p.a_stages;
-  while (p.a_stages * p.a_stage_bytes + p.b_stages * b_stage > 210 * 1024 && p.b_stages > 2) --p.b_stages;
+  const uint32_t ring_budget = 200 * 1024;
+  while (p.a_stages > 2 && p.a_stages * p.a_stage_bytes + 2 * b_stage > ring_budget) --p.a_stages;
+  int bs = static_cast<int>((ring_budget - p.a_stages * p.a_stage_bytes) / b_stage);
+  p.b_stages = bs > 16 ? 16 : (bs < 2 ? 2 : bs);
   p.ebias = d->ebias;
   p.ebias_stride = d->ebias_stride;
   p.out_planar = d->out_planar;

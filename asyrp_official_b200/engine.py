@@ -218,7 +218,7 @@ class Plan:
         t = self.pool.alloc((self.N, H, W, C), torch.float16)
         st = None
         if stats:
-            st = self.pool.alloc((self.N, ops.conv_stats_tiles(self.N, H, W, C, has_3x3), C // 2, 2), torch.float32)
+            st = self.pool.alloc((self.N, ops.conv_stats_tiles(H, W, C, has_3x3), C // 2, 2), torch.float32)
         return Act(t, st)
 
     def _free(self, act):

@@ -39,14 +39,14 @@ def pack_conv_weight(w):
     return w.permute(0, 2, 3, 1).reshape(o, -1).to(torch.float16).contiguous()
 
 
-def conv_stats_tiles(N, H, W, C, has_3x3):
-    return _lib.load().asyrp_conv_stats_tiles(N, H, W, C, int(has_3x3))
+def conv_stats_tiles(H, W, C, has_3x3):
+    return _lib.load().asyrp_conv_stats_tiles(H, W, C, int(has_3x3))
 
 
 def new_stats(N, H, W, C, device, has_3x3):
     """Partial GroupNorm sums written by a conv epilogue: [N][tiles][C/2][2] fp32.  The tile geometry depends on
     whether the producing conv has a 3x3 stride-1 segment."""
-    return torch.zeros(N, conv_stats_tiles(N, H, W, C, has_3x3), C // 2, 2, dtype=torch.float32, device=device)
+    return torch.zeros(N, conv_stats_tiles(H, W, C, has_3x3), C // 2, 2, dtype=torch.float32, device=device)
 
 
 class ConvOp:

@@ -77,7 +77,7 @@ typedef struct AsyrpConvDesc {
 
 /* number of tile slots of the stats buffer of a conv with this output geometry; has_3x3: the conv has an
  * ASYRP_CONV_3x3 segment (selects the 8x16 halo tile geometry when H%16==0 and W%8==0) */
-int asyrp_conv_stats_tiles(int N, int H, int W, int Cout, int has_3x3);
+int asyrp_conv_stats_tiles(int H, int W, int Cout, int has_3x3);
 int asyrp_conv_create(const AsyrpConvDesc* desc, void** op); /* encodes TMA descriptors; host only */
 int asyrp_conv_launch(void* op, void* stream);
 int asyrp_conv_set_scales(void* op, float acc_scale, float res_scale); /* hs_coeff of forward(), diffusion.py:512-516 */

@@ -24,9 +24,9 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     assert lib.asyrp_last_error() is not None
     # pure host helper (no device): tile bookkeeping for the GroupNorm partial sums
-    assert lib.asyrp_conv_stats_tiles(16, 256, 256, 256, 0) == 512  # 128x256 tiles
-    assert lib.asyrp_conv_stats_tiles(16, 256, 256, 128, 1) == 512  # swapped 128x256 tiles, two slots each
-    assert lib.asyrp_conv_stats_tiles(16, 8, 8, 512, 1) == 4        # 2 samples per tile, one slot per lane quarter
+    assert lib.asyrp_conv_stats_tiles(256, 256, 256, 0) == 512  # 128x256 tiles
+    assert lib.asyrp_conv_stats_tiles(256, 256, 128, 1) == 512  # swapped 128x256 tiles, two slots each
+    assert lib.asyrp_conv_stats_tiles(8, 8, 512, 1) == 4        # 2 samples per tile, one slot per lane quarter
 
 
 def test_no_cpu_fallback():
