@@ -45,7 +45,7 @@ SIGNATURES = {
     "asyrp_conv_destroy": (None, [c_void_p]),
     "asyrp_gn_finalize": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_float,
                                   c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
-    "asyrp_apply": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+    "asyrp_apply": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int,
                             c_int, c_void_p]),
     "asyrp_pack_input": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "asyrp_timestep_embedding": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),

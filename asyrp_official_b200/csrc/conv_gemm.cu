@@ -637,13 +637,13 @@ static int conv_halo_ok(int H, int W) { return H % 16 == 0 && W % 8 == 0; }
 // Tile configuration: BN output channels x MT sub-tiles of 128 pixels per CTA tile.  Larger tiles re-use operands
 // better (BN=256, or the swapped-operand 128x256 variant for BN=128/MT=2: TMEM holds 2*MT*BN <= 512 fp32 columns);
 // small layers instead need enough tiles to occupy the 148 SMs.  Pick the most efficient configuration that still
-// yields ~a full wave of tiles at a NOMINAL batch of 8, else the one with the most tiles.  The choice must not
+// yields ~a full wave of tiles at a NOMINAL batch of 16, else the one with the most tiles.  The choice must not
 // depend on the actual batch: the tile partition fixes the summation order of the GroupNorm partial sums, and a
 // sample's result has to be bit-identical whatever batch (or batch shard on another GPU) it is part of.
 static void conv_config(int H, int W, int Cout, int halo, int* BN, int* MT) {
   int TW, TH, NB;
   conv_tile_shape(H, W, halo, &TW, &TH, &NB);
-  constexpr int kNominalBatch = 8;
+  constexpr int kNominalBatch = 16;
   const int tiles_x = (W + TW - 1) / TW, tiles_n = (kNominalBatch + NB - 1) / NB;
   const int cand[5][2] = {{256, 1}, {128, 2}, {128, 1}, {64, 2}, {64, 1}};  // by decreasing operand re-use
   int best = -1, best_tiles = -1;

@@ -84,7 +84,8 @@ __global__ void gn_finalize_kernel(const float* __restrict__ st_a, int Ca, int T
 struct ApplyParams {
   const __half* src_a; int Ca;
   const __half* src_b; int Cb;
-  const float* affine;  // [N][C][2] or nullptr (identity)
+  const float* affine;  // (a, b) pairs of the source channels, row n at affine + n*aff_stride floats; nullptr = identity
+  int aff_stride;
   __half* out;
   int N, Hi, Wi, Ho, Wo;
   int act, resample;
@@ -126,7 +127,7 @@ __global__ void __launch_bounds__(256) apply_kernel(const ApplyParams p) {
   __half* dst = p.out + static_cast<size_t>(n) * p.Ho * p.Wo * C + c;
   float a[8], b[8];
   if (p.affine != nullptr) {
-    const float4* ap = reinterpret_cast<const float4*>(p.affine + (static_cast<size_t>(n) * C + c) * 2);
+    const float4* ap = reinterpret_cast<const float4*>(p.affine + static_cast<size_t>(n) * p.aff_stride + c * 2);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const float4 t = ap[k];
@@ -327,13 +328,14 @@ ASYRP_API int asyrp_gn_finalize(const float* st_a, int Ca, int Ta, const float* 
   return ASYRP_OK;
 }
 
-ASYRP_API int asyrp_apply(const void* src_a, int Ca, const void* src_b, int Cb, const float* affine, void* out,
-                          int N, int Hi, int Wi, int act, int resample, void* stream) {
+ASYRP_API int asyrp_apply(const void* src_a, int Ca, const void* src_b, int Cb, const float* affine,
+                          int affine_stride, void* out, int N, int Hi, int Wi, int act, int resample, void* stream) {
   ASYRP_REQUIRE(Ca % 8 == 0 && Cb % 8 == 0, "asyrp_apply: channels must be multiples of 8");
   ApplyParams p;
   p.src_a = static_cast<const __half*>(src_a); p.Ca = Ca;
   p.src_b = static_cast<const __half*>(src_b); p.Cb = Cb;
-  p.affine = affine; p.out = static_cast<__half*>(out);
+  p.affine = affine; p.aff_stride = affine_stride > 0 ? affine_stride : (Ca + Cb) * 2;
+  p.out = static_cast<__half*>(out);
   p.N = N; p.Hi = Hi; p.Wi = Wi;
   p.Ho = resample == 1 ? Hi / 2 : (resample == 2 ? Hi * 2 : Hi);
   p.Wo = resample == 1 ? Wi / 2 : (resample == 2 ? Wi * 2 : Wi);

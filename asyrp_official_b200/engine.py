@@ -206,6 +206,7 @@ class Plan:
         self.et_mod = torch.zeros(N, a.out_ch, S, S, dtype=torch.float32, device=dev)
         self.enc_ops, self.delta_ops, self.dec_ops, self.dec_mod_ops = [], [], [], []
         self.scale_ops = []  # conv ops whose epilogue scales are hs_coeff
+        self._temps = []     # materialised operands to release after the next conv launch is recorded
         self._cur = self.enc_ops
         self._build()
 
@@ -238,14 +239,14 @@ class Plan:
                    nbytes=4.0 * (a.stats.numel() + (b.stats.numel() if b else 0) + aff.numel()))
         return aff
 
-    def _apply(self, srcs, affine, act, resample=RESAMPLE_NONE):
+    def _apply(self, srcs, affine, act, resample=RESAMPLE_NONE, affine_offset=0):
         a, b = srcs[0], (srcs[1] if len(srcs) > 1 else None)
         C = sum(s.C for s in srcs)
         H = a.H // 2 if resample == RESAMPLE_AVGPOOL2 else (a.H * 2 if resample == RESAMPLE_UP2 else a.H)
         Wd = a.W // 2 if resample == RESAMPLE_AVGPOOL2 else (a.W * 2 if resample == RESAMPLE_UP2 else a.W)
         out = self._act(H, Wd, C, stats=False)
         n_in = out.t.numel() * (4 if resample == RESAMPLE_AVGPOOL2 else (0.25 if resample == RESAMPLE_UP2 else 1))
-        self._emit(lambda: ops.apply(a.t, b.t if b else None, affine, out.t, act, resample), "apply",
+        self._emit(lambda: ops.apply(a.t, b.t if b else None, affine, out.t, act, resample, affine_offset), "apply",
                    nbytes=2.0 * (n_in + out.t.numel()))
         return out
 
@@ -270,14 +271,26 @@ class Plan:
         return out, op
 
     # ------------------------------------------------------------------ blocks
-    @staticmethod
-    def _fused(srcs, mode, aff, act):
-        """conv segments over the channel concat of `srcs` with the GroupNorm affine (+SiLU) fused into the operand"""
+    def _fused(self, srcs, mode, aff, act):
+        """conv segments over the channel concat of `srcs` with the GroupNorm affine (+SiLU) fused into the operand.
+        Layers smaller than 16x16 keep the pointwise kernel: their K loop is a chain of short stages, and the in-kernel
+        transform (one stage at a time) would sit on the critical path; the tensors are ~1 MB."""
         segs, off = [], 0
+        small = srcs[0].H < 16
         for s_ in srcs:
-            segs.append((s_, mode, aff, off, act))
+            if small:
+                a_ = self._apply([s_], aff, act, affine_offset=off)
+                self._temps.append(a_)
+                segs.append((a_, mode))
+            else:
+                segs.append((s_, mode, aff, off, act))
             off += s_.C
         return segs
+
+    def _drop_temps(self):
+        for a_ in self._temps:
+            self._free(a_)
+        self._temps = []
 
     def _res_block(self, layer: Res, srcs):
         """ResnetBlock (ddpm/diffusion.py:151-170) / ResBlock (improved_ddpm/unet.py:278-298): two fused
@@ -320,6 +333,7 @@ class Plan:
         self._free(h)
         if xr is not None:
             self._free(xr)
+        self._drop_temps()
         return out
 
     def _attn_block(self, layer: Attn, x):
@@ -331,6 +345,7 @@ class Plan:
         qkv, _ = self._conv(self._fused([x], MODE_1x1, aff, 0), W[p + ".wqkv"], 3 * C, x.H, x.W, ebias=W[p + ".bqkv"],
                             stats=False)
         self.pool.release(aff)
+        self._drop_temps()
         att = self._act(x.H, x.W, C, stats=False)
         N, T = self.N, x.H * x.W
         scale = float(d) ** -0.5  # C^-0.5 (ddpm/diffusion.py:213) == (d^-1/4)^2 (improved_ddpm/unet.py:389-392)
@@ -446,6 +461,7 @@ class Plan:
         self.scale_ops.append((op, i))
         self.pool.release(aff)
         self._free(d1)
+        self._drop_temps()
         if h2_prev is not h:
             self._free(h2_prev)
         return h2
@@ -462,6 +478,7 @@ class Plan:
                    stats=False, planar=out_planar, algo_flops=2.0 * self.N * h.H * h.W * a.out_ch * 9 * h.C)
         self.pool.release(aff)
         self._free(h)
+        self._drop_temps()
 
     # ------------------------------------------------------------------ execution
     def set_coeffs(self, hs_coeff):

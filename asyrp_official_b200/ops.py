@@ -127,11 +127,17 @@ def gn_finalize(stats_a, Ca, stats_b, Cb, gamma, beta, eps, N, HW, affine, scale
                                 _ptr(scale_shift), ss_stride, _ptr(affine), _stream()), "asyrp_gn_finalize")
 
 
-def apply(src_a, src_b, affine, out, act, resample=RESAMPLE_NONE):
+def apply(src_a, src_b, affine, out, act, resample=RESAMPLE_NONE, affine_offset=0):
+    """out = resample(act(a*x+b)); affine [N][Ctot][2] may cover more channels than the sources: the sources' first
+    channel is `affine_offset` within it"""
     lib = _lib.load()
     N, Hi, Wi, Ca = src_a.shape
     Cb = src_b.shape[-1] if src_b is not None else 0
-    check(lib.asyrp_apply(_ptr(src_a), Ca, _ptr(src_b), Cb, _ptr(affine), _ptr(out), N, Hi, Wi, int(act),
+    aptr, astride = None, 0
+    if affine is not None:
+        aptr = C.c_void_p(affine.data_ptr() + affine_offset * 2 * 4)
+        astride = affine.shape[1] * 2
+    check(lib.asyrp_apply(_ptr(src_a), Ca, _ptr(src_b), Cb, aptr, astride, _ptr(out), N, Hi, Wi, int(act),
                           resample, _stream()), "asyrp_apply")
 
 

@@ -94,9 +94,10 @@ int asyrp_gn_finalize(const float* stats_a, int Ca, int tiles_a, const float* st
 
 /* ---- out = resample(act(a*x + b)) over the channel concat of up to two NHWC fp16 sources ------------------
  * act: 0 identity, 1 SiLU (x*sigmoid(x), ddpm/diffusion.py:63-65).  resample: 0 none, 1 2x2 average pool
- * (improved_ddpm/unet.py:173-181), 2 nearest x2 (F.interpolate, ddpm/diffusion.py:83-84).  affine NULL = identity. */
-int asyrp_apply(const void* src_a, int Ca, const void* src_b, int Cb, const float* affine, void* out, int N, int Hi,
-                int Wi, int act, int resample, void* stream);
+ * (improved_ddpm/unet.py:173-181), 2 nearest x2 (F.interpolate, ddpm/diffusion.py:83-84).  affine: (a, b) pairs of
+ * the Ca+Cb channels, row n at affine + n*affine_stride floats (0: rows of (Ca+Cb)*2); NULL = identity. */
+int asyrp_apply(const void* src_a, int Ca, const void* src_b, int Cb, const float* affine, int affine_stride,
+                void* out, int N, int Hi, int Wi, int act, int resample, void* stream);
 
 /* x_t fp32 NCHW [N][Cin<=64][H][W] -> fp16 NHWC [N][H][W][64] (zero padded channels): operand of conv_in */
 int asyrp_pack_input(const float* x, void* out, int N, int Cin, int H, int W, void* stream);
