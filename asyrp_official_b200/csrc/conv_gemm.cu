@@ -299,18 +299,53 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
               if (sg.affine != nullptr) {
                 uint8_t* stage = sA + sa * p.a_stage_bytes;
                 const int xoff = sg.mode == 3 ? -1 : (sg.mode == 1 ? cp - 1 : 0);
-                // (hy, r) = (tile row, position inside the row) of pixel px, advanced incrementally (no divisions)
-                int hy = pl / prow, r = pl - hy * prow;
-                const int dhy = kLanes / prow, dr = kLanes - dhy * prow;
-#pragma unroll 2
-                for (int px = pl; px < npix; px += kLanes) {
-                  int nn = 0, xx = r;
-                  if (p.NB != 1) { nn = r / pw; xx = r - nn * pw; }
-                  const int x = x0 + xx + xoff, y = y0 + hy + yoff, n = n0 + nn;
-                  uint4* slot = reinterpret_cast<uint4*>(stage + px * 128 + ((jl ^ (px & 7)) << 4));
-                  uint4 u = make_uint4(0u, 0u, 0u, 0u);
-                  if (x >= 0 && x < p.W && y >= 0 && y < p.H && n < p.N) {
-                    if (p.NB != 1) {
+                if (p.NB == 1) {
+                  // 4 pixels in flight per thread: all shared-memory loads first, branch-free math, then the stores.
+                  // (hy, r) = (tile row, position inside the row) of pixel px, advanced incrementally (no divisions)
+                  int hy = pl / prow, r = pl - hy * prow;
+                  const int dhy = kLanes / prow, dr = kLanes - dhy * prow;
+                  for (int px = pl; px < npix; px += 4 * kLanes) {
+                    uint4 u[4];
+                    bool ok[4], inimg[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                      const int pk = px + k * kLanes;
+                      ok[k] = pk < npix;
+                      const int x = x0 + r + xoff, y = y0 + hy + yoff;
+                      inimg[k] = ok[k] && x >= 0 && x < p.W && y >= 0 && y < p.H && n0 < p.N;
+                      u[k] = make_uint4(0u, 0u, 0u, 0u);
+                      if (ok[k]) u[k] = *reinterpret_cast<const uint4*>(stage + pk * 128 + ((jl ^ (pk & 7)) << 4));
+                      hy += dhy;
+                      r += dr;
+                      if (r >= prow) { r -= prow; ++hy; }
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                      __half2* h2 = reinterpret_cast<__half2*>(&u[k]);
+#pragma unroll
+                      for (int e = 0; e < 4; ++e) {
+                        float2 f = __half22float2(h2[e]);
+                        f.x = fmaf(ca[2 * e], f.x, cb[2 * e]);
+                        f.y = fmaf(ca[2 * e + 1], f.y, cb[2 * e + 1]);
+                        if (sg.act) { f.x = silu_fast(f.x); f.y = silu_fast(f.y); }
+                        h2[e] = inimg[k] ? __floats2half2_rn(f.x, f.y) : __floats2half2_rn(0.f, 0.f);
+                      }
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                      const int pk = px + k * kLanes;
+                      if (ok[k]) *reinterpret_cast<uint4*>(stage + pk * 128 + ((jl ^ (pk & 7)) << 4)) = u[k];
+                    }
+                  }
+                } else {
+                  // tiles spanning several samples (layers below 16x16 when fused): per-pixel sample lookup
+                  for (int px = pl; px < npix; px += kLanes) {
+                    const int hy = px / prow, r = px - hy * prow;
+                    const int nn = r / pw, xx = r - nn * pw;
+                    const int x = x0 + xx + xoff, y = y0 + hy + yoff, n = n0 + nn;
+                    uint4* slot = reinterpret_cast<uint4*>(stage + px * 128 + ((jl ^ (px & 7)) << 4));
+                    uint4 u = make_uint4(0u, 0u, 0u, 0u);
+                    if (x >= 0 && x < p.W && y >= 0 && y < p.H && n < p.N) {
                       const float4* ap = reinterpret_cast<const float4*>(
                           sg.affine + static_cast<size_t>(n) * sg.aff_stride + (ch * 64 + jl * 8) * 2);
 #pragma unroll
@@ -318,25 +353,19 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
                         const float4 t4 = ap[k];
                         ca[2 * k] = t4.x; cb[2 * k] = t4.y; ca[2 * k + 1] = t4.z; cb[2 * k + 1] = t4.w;
                       }
-                    }
-                    u = *slot;
-                    __half2* h2 = reinterpret_cast<__half2*>(&u);
+                      u = *slot;
+                      __half2* h2 = reinterpret_cast<__half2*>(&u);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                      float2 f = __half22float2(h2[k]);
-                      f.x = fmaf(ca[2 * k], f.x, cb[2 * k]);
-                      f.y = fmaf(ca[2 * k + 1], f.y, cb[2 * k + 1]);
-                      if (sg.act) {
-                        f.x = __fdividef(f.x, 1.0f + __expf(-f.x));
-                        f.y = __fdividef(f.y, 1.0f + __expf(-f.y));
+                      for (int k = 0; k < 4; ++k) {
+                        float2 f = __half22float2(h2[k]);
+                        f.x = fmaf(ca[2 * k], f.x, cb[2 * k]);
+                        f.y = fmaf(ca[2 * k + 1], f.y, cb[2 * k + 1]);
+                        if (sg.act) { f.x = silu_fast(f.x); f.y = silu_fast(f.y); }
+                        h2[k] = __floats2half2_rn(f.x, f.y);
                       }
-                      h2[k] = __floats2half2_rn(f.x, f.y);
                     }
+                    *slot = u;
                   }
-                  *slot = u;
-                  hy += dhy;
-                  r += dr;
-                  if (r >= prow) { r -= prow; ++hy; }
                 }
                 fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
               }

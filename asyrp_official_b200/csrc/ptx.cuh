@@ -146,5 +146,13 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+// branch-free SiLU on the SFU: x * rcp(1 + 2^(-x*log2e)); relative error ~2^-21 (the result is rounded to fp16).
+// x -> -inf gives x*0 = -0, x -> +inf gives x*1.
+__device__ __forceinline__ float silu_fast(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return x * r;
+}
 
 }  // namespace asyrp

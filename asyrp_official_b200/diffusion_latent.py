@@ -125,15 +125,47 @@ class Asyrp(object):
             out[mode] = pairs
         return out
 
-    def _load_latent_pairs(self):
-        """precomputed/<category>_<mode>_t<t_0>_nim<N>_ninv<k>_pairs.pth written by the reference (:974-982,1082)"""
+    @torch.no_grad()
+    def invert_batch(self, model, x0, n_inv_step=None):
+        """DDIM inversion x_0 -> x_T followed by the deterministic reconstruction x_T -> x_rec, both as graph replays
+        (precompute_pairs, diffusion_latent.py:1028-1072).  Returns (x_T, x_rec) on the host."""
+        a = self.args
+        n = n_inv_step or a.n_inv_step
+        seq_inv = [int(s + 1e-6) for s in list(np.linspace(0, 1, n) * a.t_0)]
+        seq_inv_next = [-1] + list(seq_inv[:-1])
+        eng = model.engine
+        x_lat = eng.sample(x0.to(eng.device), Schedule.inversion(self.betas, seq_inv, seq_inv_next))
+        x_rec = eng.sample(x_lat, Schedule(self.betas, seq_inv, seq_inv_next, t_edit=10 ** 9, t_addnoise=0,
+                                           hs_coeff=(1.0,), edit=False))
+        return x_lat.cpu(), x_rec.cpu()
+
+    @torch.no_grad()
+    def precompute_pairs(self, model, save_imgs=False):
+        """[x0, x_rec, x_T] triples per image, cached as precomputed/<category>_<mode>_t<t_0>_nim<N>_ninv<k>_pairs.pth
+        — the reference's file name and list-of-triples format (:974-982,1072,1082).  Images come from
+        --custom_train_dataset_dir / --custom_test_dataset_dir (png/jpg, resized to image_size, scaled to [-1, 1]);
+        the reference's LMDB dataset classes are out of scope."""
         a, out = self.args, {}
+        os.makedirs('precomputed', exist_ok=True)
         for mode, n in (("train", a.n_train_img), ("test", a.n_test_img)):
             p = os.path.join('precomputed/', f'{self.config.data.category}_{mode}_t{a.t_0}_nim{n}_ninv{a.n_inv_step}_pairs.pth')
-            if not os.path.exists(p):
-                raise FileNotFoundError(f"{p}: DDIM inversion (precompute_pairs) is not part of this build; use "
-                                        "--load_random_noise or provide the latent cache")
-            out[mode] = torch.load(p, map_location="cpu", weights_only=True)
+            if os.path.exists(p) and not getattr(a, "re_precompute", False):
+                out[mode] = torch.load(p, map_location="cpu", weights_only=True)
+                continue
+            folder = getattr(a, f"custom_{mode}_dataset_dir", None)
+            if not folder or not os.path.isdir(folder):
+                raise FileNotFoundError(f"{p} not found and --custom_{mode}_dataset_dir is not a directory: nothing to "
+                                        "invert (use --load_random_noise for random latents)")
+            imgs = _load_image_folder(folder, self.config.data.image_size, n)
+            pairs = []
+            bs = max(1, a.bs_train)
+            for k in range(0, len(imgs), bs):
+                x0 = torch.cat(imgs[k:k + bs], dim=0)
+                x_lat, x_rec = self.invert_batch(model, x0)
+                for i in range(x0.shape[0]):
+                    pairs.append([x0[i:i + 1].clone(), x_rec[i:i + 1].clone(), x_lat[i:i + 1].clone()])
+            torch.save(pairs, p)
+            out[mode] = pairs
         return out
 
     # ------------------------------------------------------------------------------------------
@@ -239,7 +271,7 @@ class Asyrp(object):
         if self.world > 1 and torch.distributed.is_initialized():
             broadcast_weights(model)
         # ----------- x_T
-        pairs = self.random_noise_pairs(model) if a.load_random_noise else self._load_latent_pairs()
+        pairs = self.random_noise_pairs(model) if a.load_random_noise else self.precompute_pairs(model)
         results = {}
         for mode, do, n_img in (("train", a.do_train, a.n_train_img), ("test", a.do_test, a.n_test_img)):
             if not do:
@@ -277,6 +309,17 @@ def broadcast_weights(model, src=0):
         p.data.copy_(flat[off:off + n].view_as(p))
         off += n
     model.refresh_weights()
+
+
+def _load_image_folder(folder, size, limit):
+    from PIL import Image
+    names = sorted(f for f in os.listdir(folder) if f.lower().endswith((".png", ".jpg", ".jpeg")))[:limit]
+    out = []
+    for f in names:
+        im = Image.open(os.path.join(folder, f)).convert("RGB").resize((size, size), Image.BICUBIC)
+        t = torch.from_numpy(np.asarray(im).copy()).permute(2, 0, 1).float() / 255.0
+        out.append((t * 2.0 - 1.0)[None])  # rescaled to [-1, 1] (config.data.rescaled)
+    return out
 
 
 def _read_tsv(path):

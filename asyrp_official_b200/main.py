@@ -75,6 +75,9 @@ def build_parser():
     p.add_argument('--n_test_img', type=int, default=10)
     p.add_argument('--model_path', type=str, default=None)
     p.add_argument('--get_h_num', type=int, default=0)
+    p.add_argument('--re_precompute', **sa)
+    p.add_argument('--custom_train_dataset_dir', type=str, default="./custom/train")
+    p.add_argument('--custom_test_dataset_dir', type=str, default="./custom/test")
     p.add_argument('--dt_lambda', type=float, default=1.0)
     p.add_argument('--dt_end', type=int, default=950)
     p.add_argument('--n_iter', type=int, default=1)

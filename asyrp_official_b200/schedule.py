@@ -30,13 +30,13 @@ def make_sequences(t_0=999, n_step=40):
 
 
 class Schedule:
-    def __init__(self, betas, seq, seq_next, t_edit, t_addnoise=0, hs_coeff=(1.0, 1.0), edit=True):
+    def __init__(self, betas, seq, seq_next, t_edit, t_addnoise=0, hs_coeff=(1.0, 1.0), edit=True, pairs=None):
         """betas: fp32 tensor (Asyrp.betas).  Coefficients are evaluated with the same fp32 torch expressions as
         utils/diffusion_utils.py:66-97 (cumprod in fp32 on the host) so that they are bit-identical to the CPU oracle."""
         b = torch.as_tensor(betas, dtype=torch.float32).cpu()
         ac = (1.0 - b).cumprod(dim=0)
         steps: List[Step] = []
-        for i, j in zip(reversed(seq), reversed(seq_next)):
+        for i, j in (pairs if pairs is not None else zip(reversed(seq), reversed(seq_next))):
             at = ac[i]
             an = torch.ones_like(at) if j == -1 else ac[j]
             eta = 1.0 if i < t_addnoise else 0.0
@@ -50,6 +50,13 @@ class Schedule:
         self.steps = steps
         self.hs_coeff: Tuple[float, ...] = tuple(float(c) for c in hs_coeff)
         self.t_edit, self.t_addnoise = t_edit, t_addnoise
+
+    @classmethod
+    def inversion(cls, betas, seq, seq_next):
+        """DDIM inversion x_0 -> x_T: the deterministic step applied with t < t_next, plain UNet (index=None)
+        (precompute_pairs, diffusion_latent.py:1032-1044: zip(seq_inv_next[1:], seq_inv[1:]))"""
+        return cls(betas, None, None, t_edit=10 ** 9, t_addnoise=0, hs_coeff=(1.0,), edit=False,
+                   pairs=list(zip(seq_next[1:], seq[1:])))
 
     def key(self):
         return (tuple(self.steps), self.hs_coeff)

@@ -143,6 +143,25 @@ def mini(family):
     out["traj_x0"] = xf.numpy()
     out["traj_x0t"] = np.stack([r[1].numpy() for r in rec])
     out["traj_noise_seed"] = np.array(4321)
+    # DDIM inversion x_0 -> x_T and deterministic reconstruction with the plain UNet (precompute_pairs,
+    # diffusion_latent.py:1032-1072): reference denoising_step with t < t_next, index=None
+    x0img = torch.tanh(synth.synth_noise((B, 3, S, S), seed=77))
+    logv = None if learn_sigma else o_smp.make_logvar(o_smp.get_beta_schedule(beta_start=1e-4, beta_end=0.02,
+                                                                             num_diffusion_timesteps=1000))
+    xr, xo_ = x0img.clone(), x0img.clone()
+    for i, j in zip(seq_next[1:], seq[1:]):
+        t, tn = torch.ones(B) * i, torch.ones(B) * j
+        xr = ref_du.denoising_step(xr, t=t, t_next=tn, models=model, logvars=logv, sampling_type="ddim", b=betas, eta=0,
+                                   learn_sigma=learn_sigma)[0]
+        xo_ = o_smp.denoising_step(xo_, t, tn, model=lambda *a, **k: fwd(sd, *a, **k), logvars=logv, b=betas, eta=0.0,
+                                   learn_sigma=learn_sigma)[0]
+    assert torch.equal(xr, xo_), (xr - xo_).abs().max()
+    out["inv_x0"], out["inv_xT"] = x0img.numpy(), xr.numpy()
+    for i, j in zip(reversed(seq), reversed(seq_next)):
+        t, tn = torch.ones(B) * i, torch.ones(B) * j
+        xr = ref_du.denoising_step(xr, t=t, t_next=tn, models=model, logvars=logv, sampling_type="ddim", b=betas,
+                                   learn_sigma=learn_sigma)[0]
+    out["inv_rec"] = xr.numpy()
     np.savez_compressed(os.path.join(HERE, f"{family}_mini.npz"), **out)
     print(f"{family}_mini ok: |x_final|max={xf.abs().max():.3f}")
 

@@ -99,3 +99,19 @@ def test_full_size_forward_matches_reference(name, family, cfg):
     for key, a in zip(("et", "et_mod", "delta_h", "middle_h"), out):
         _close(a[..., ::4, ::4] if a.shape[-1] == 256 else a, gold[key], f"{name} {key}")
         assert abs(a.abs().max().item() - float(gold[key + "_absmax"])) <= TOL * 10
+
+
+@pytest.mark.parametrize("family", ["ddpm", "adm"])
+def test_mini_inversion_matches_reference(family):
+    """DDIM inversion (t < t_next, index=None) through the oracle's denoising_step vs the reference's"""
+    gold = np.load(os.path.join(G, f"{family}_mini.npz"))
+    cfg, sd, fwd, learn_sigma = _mini(family)
+    betas = o_smp.make_betas()
+    seq, seq_next = o_smp.make_sequences(999, 10)
+    logv = None if learn_sigma else o_smp.make_logvar(o_smp.get_beta_schedule(beta_start=1e-4, beta_end=0.02,
+                                                                             num_diffusion_timesteps=1000))
+    x = torch.from_numpy(gold["inv_x0"])
+    for i, j in zip(seq_next[1:], seq[1:]):
+        x = o_smp.denoising_step(x, torch.ones(2) * i, torch.ones(2) * j, model=fwd, logvars=logv, b=betas, eta=0.0,
+                                 learn_sigma=learn_sigma)[0]
+    _close(x, gold["inv_xT"], f"{family} inversion")
