@@ -302,6 +302,68 @@ __global__ void unpack_nchw_kernel(const __half* __restrict__ in, float* __restr
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Explicit delta_h injection (DiffStyle / raw-delta_h checkpoints): h2 = slerp(t, h, |h| * dh / |dh|), per sample
+// over all C*H*W elements (models/ddpm/diffusion.py:6-40,528-539); with use_mask the interpolation is restricted to
+// rows 4..H-2, columns 3..4 without norm matching and h is kept elsewhere (:519-527).
+// One block per sample.  h: fp16 NHWC; dh: fp32 NCHW (sample stride dh_stride, 0 = shared); writes h2 (fp16 NHWC)
+// and its GroupNorm partial sums into tile slot 0 of `stats` ([N][T][C/2][2]; other slots zeroed).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float block_sum(float v, float* sh) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  float t = 0.f;
+  for (int i = 0; i < (blockDim.x >> 5); ++i) t += sh[i];
+  return t;
+}
+
+__global__ void __launch_bounds__(256) slerp_h_kernel(const __half* __restrict__ h, const float* __restrict__ dh,
+                                                      long long dh_stride, __half* __restrict__ h2,
+                                                      float* __restrict__ stats, int T, int C, int H, int W, float t,
+                                                      int use_mask) {
+  __shared__ float sh[8];
+  const int n = blockIdx.x, HW = H * W;
+  const __half* hn = h + static_cast<size_t>(n) * HW * C;
+  const float* dn = dh + static_cast<size_t>(n) * dh_stride;
+  __half* on = h2 + static_cast<size_t>(n) * HW * C;
+  float shh = 0.f, sdd = 0.f, shd = 0.f;
+  for (int i = threadIdx.x; i < HW * C; i += blockDim.x) {
+    const int pix = i / C, c = i - pix * C;
+    const int y = pix / W, x = pix - y * W;
+    const float m = use_mask ? ((y >= 4 && y < H - 1 && x >= 3 && x < 5) ? 1.f : 0.f) : 1.f;
+    const float a = __half2float(hn[i]) * m, b = dn[static_cast<size_t>(c) * HW + pix] * m;
+    shh += a * a; sdd += b * b; shd += a * b;
+  }
+  shh = block_sum(shh, sh); sdd = block_sum(sdd, sh); shd = block_sum(shd, sh);
+  const float nh = sqrtf(shh), nd = sqrtf(sdd);
+  const float th0 = acosf(shd / (nh * nd));
+  const float s0 = sinf(th0 - th0 * t) / sinf(th0), s1 = sinf(th0 * t) / sinf(th0);
+  const float dscale = use_mask ? 1.f : nh / nd;  // v1 = |h| * dh / |dh| (norm-matched) unless masked
+  // second pass: h2 and its channel-pair statistics; a thread owns channel pairs, pixels in the inner loop
+  float* st = stats + static_cast<size_t>(n) * T * (C / 2) * 2;
+  for (int pr = threadIdx.x; pr < C / 2; pr += blockDim.x) {
+    float s = 0.f, ss = 0.f;
+    for (int pix = 0; pix < HW; ++pix) {
+      const int y = pix / W, x = pix - y * W;
+      const bool in = !use_mask || (y >= 4 && y < H - 1 && x >= 3 && x < 5);
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int c = pr * 2 + k;
+        const float a = __half2float(hn[static_cast<size_t>(pix) * C + c]);
+        const float b = dn[static_cast<size_t>(c) * HW + pix];
+        const float v = in ? s0 * a + s1 * dscale * b : a;
+        on[static_cast<size_t>(pix) * C + c] = __float2half_rn(v);
+        s += v; ss += v * v;
+      }
+    }
+    st[pr * 2] = s; st[pr * 2 + 1] = ss;
+    for (int tt = 1; tt < T; ++tt) { st[(tt * (C / 2) + pr) * 2] = 0.f; st[(tt * (C / 2) + pr) * 2 + 1] = 0.f; }
+  }
+}
+
 }  // namespace asyrp
 
 using namespace asyrp;
@@ -413,6 +475,16 @@ ASYRP_API int asyrp_unpack_nchw(const void* in, float* out, int N, int C, int HW
   const size_t total = static_cast<size_t>(N) * C * HW;
   unpack_nchw_kernel<<<grid_for(total, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __half*>(in), out, N, C, HW);
+  ASYRP_CHECK_CUDA(cudaGetLastError());
+  return ASYRP_OK;
+}
+
+ASYRP_API int asyrp_slerp_h(const void* h, const float* dh, long long dh_sample_stride, void* h2, float* stats,
+                            int stats_tiles, int N, int C, int H, int W, float t, int use_mask, void* stream) {
+  ASYRP_REQUIRE(C % 2 == 0 && stats_tiles >= 1, "asyrp_slerp_h: bad arguments");
+  slerp_h_kernel<<<N, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __half*>(h), dh, dh_sample_stride,
+                                                                    static_cast<__half*>(h2), stats, stats_tiles, C, H,
+                                                                    W, t, use_mask);
   ASYRP_CHECK_CUDA(cudaGetLastError());
   return ASYRP_OK;
 }

@@ -192,8 +192,29 @@ class Asyrp(object):
         return x0.cpu()
 
     @torch.no_grad()
+    def _edit_batch_explicit(self, model, x_lat, seq, seq_next, hs_coeff, delta_h_dict):
+        """the reference's step loop (diffusion_latent.py:501-520) for raw-Δh checkpoints: delta_h = dict[t] for
+        t >= t_edit (dict[0] with --ignore_timesteps), through the explicit-Δh branch of forward()"""
+        from .utils.diffusion_utils import denoising_step
+        a = self.args
+        x = x_lat.to(self.device)
+        bs = x.shape[0]
+        for i, j in zip(reversed(seq), reversed(seq_next)):
+            t, t_next = torch.ones(bs) * i, torch.ones(bs) * j
+            dh = None
+            if i >= self.t_edit:
+                dh = delta_h_dict[0] if getattr(a, "ignore_timesteps", False) else delta_h_dict[int(i)]
+            x, _, _, _ = denoising_step(x, t, t_next, models=model, logvars=self.logvar, b=self.betas,
+                                        sampling_type=a.sample_type, learn_sigma=self.learn_sigma,
+                                        index=max(a.get_h_num, 1) - 1, eta=1.0 if i < self.t_addnoise else 0.0,
+                                        t_edit=self.t_edit, hs_coeff=hs_coeff, delta_h=dh,
+                                        ignore_timestep=getattr(a, "ignore_timesteps", False),
+                                        dt_lambda=a.dt_lambda, dt_end=getattr(a, "dt_end", 999))
+        return x.cpu()
+
+    @torch.no_grad()
     def save_image(self, model, x_lat_tensor, seq_inv, seq_inv_next, save_x0=False, save_x_origin=False,
-                   x0_tensor=None, folder_dir="", file_name="", hs_coeff=(1.0, 1.0), **_unused):
+                   x0_tensor=None, folder_dir="", file_name="", hs_coeff=(1.0, 1.0), delta_h_dict=None, **_unused):
         """rows of the grid: [x0] [origin DDIM] one row per hs_coeff tuple  (diffusion_latent.py:462-541)"""
         import torchvision.utils as tvu
         time_s = time.time()
@@ -207,7 +228,10 @@ class Asyrp(object):
         if not getattr(self.args, "pass_editing", False):
             coeffs = hs_coeff if isinstance(hs_coeff, list) else [hs_coeff]
             for tup in coeffs:
-                x_list.append(self.edit_batch(model, x_lat_tensor, self.make_schedule(seq_inv, seq_inv_next, tup)))
+                if delta_h_dict is not None:
+                    x_list.append(self._edit_batch_explicit(model, x_lat_tensor, seq_inv, seq_inv_next, tup, delta_h_dict))
+                else:
+                    x_list.append(self.edit_batch(model, x_lat_tensor, self.make_schedule(seq_inv, seq_inv_next, tup)))
         x = (torch.cat(x_list, dim=0) + 1) * 0.5
         grid = tvu.make_grid(x, nrow=self.args.bs_train, padding=1)
         os.makedirs(folder_dir, exist_ok=True)
@@ -229,9 +253,7 @@ class Asyrp(object):
         model = self.load_pretrained_model()
         if a.train_delta_block:
             model.setattr_layers(a.get_h_num)
-        if getattr(a, "train_delta_h", False):
-            raise NotImplementedError("raw delta_h checkpoints (--train_delta_h) use the explicit-Δh branch, which is "
-                                      "not built yet; DeltaBlock checkpoints (--train_delta_block) are")
+        delta_h_dict = None
         # ----------- Δh checkpoint name resolution (:594-614)
         exp_id = os.path.split(a.exp)[-1]
         if a.load_from_checkpoint:
@@ -254,7 +276,14 @@ class Asyrp(object):
         else:
             save_name_list = [save_name]
             hs_coeff = (1.0 * a.hs_coeff_origin_h, 1.0 * scaling_factor)  # :659
-        if a.train_delta_block:
+        if getattr(a, "train_delta_h", False):
+            # raw Δh checkpoint: {str(t): tensor(C,8,8)} per edit timestep, or {"0": tensor} with --ignore_timesteps
+            # (diffusion_latent.py:189-192,678-690); used through the explicit-Δh (slerp) branch, step by step
+            if not os.path.exists(save_name_list[0]):
+                raise FileNotFoundError(f"checkpoint({save_name_list[0]}) does not exist!")
+            saved = torch.load(save_name_list[0], map_location="cpu", weights_only=True)
+            delta_h_dict = {int(k): v.detach().float() for k, v in saved.items() if str(k).lstrip("-").isdigit()}
+        elif a.train_delta_block:
             if not os.path.exists(save_name_list[0]):
                 raise FileNotFoundError(f"checkpoint({save_name_list[0]}) does not exist!")
             for i in range(a.get_h_num):
@@ -289,7 +318,7 @@ class Asyrp(object):
                     results[(mode, step)] = self.save_image(
                         model, x_lat_tensor, seq_test, seq_test_next, save_x0=a.save_x0,
                         save_x_origin=a.save_x_origin, x0_tensor=x0_tensor, folder_dir=a.test_image_folder,
-                        file_name=f'{mode}_{step}_{a.n_iter - 1}', hs_coeff=hs_coeff)
+                        file_name=f'{mode}_{step}_{a.n_iter - 1}', hs_coeff=hs_coeff, delta_h_dict=delta_h_dict)
                 batch_idx += 1
                 x_lat_tensor, x0_tensor = None, None
                 if step == n_img - 1:

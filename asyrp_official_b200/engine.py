@@ -421,11 +421,20 @@ class Plan:
         h2 = h
         for i in range(eng.n_delta):
             h2 = self._delta_block(i, h, h2, last=(i == eng.n_delta - 1))
+        if h2 is h:  # no DeltaBlocks: h2 is only ever produced by the explicit-delta_h path
+            h2 = self._act(h.H, h.W, a.mid_ch, stats=True)
         self.h2 = h2
+        # explicit delta_h (DiffStyle / raw delta_h checkpoints): h2 = slerp(1-c0, h, |h| dh/|dh|), written into the same
+        # h2 buffer (+ its GroupNorm partial sums) the DeltaBlock path produces, so the decoder plan is shared
+        self.dh_user = torch.zeros(N, a.mid_ch, h.H, h.W, dtype=torch.float32, device=dev)
+        self.slerp_ops = []
+        self._cur = self.slerp_ops
+        st = eng.state
+        self._emit(lambda: ops.slerp_h(self.middle_h.t, self.dh_user, self.h2.t, self.h2.stats, st["slerp_t"],
+                                       st["use_mask"]), "slerp")
         # ---- decoders: (h2 -> et_mod) and (h -> et); same weights, same skip tensors
-        if eng.n_delta:
-            self._cur = self.dec_mod_ops
-            self._decoder(self.h2, self.et_mod)
+        self._cur = self.dec_mod_ops
+        self._decoder(self.h2, self.et_mod)
         self._cur = self.dec_ops
         self._decoder(self.middle_h, self.et)
         self.mid_f32 = torch.zeros(N, a.mid_ch, h.H, h.W, dtype=torch.float32, device=dev)
@@ -512,8 +521,8 @@ class Plan:
         for f in self.enc_ops:
             f()
 
-    def run_edit(self):
-        for f in self.delta_ops:
+    def run_edit(self, explicit=False):
+        for f in (self.slerp_ops if explicit else self.delta_ops):
             f()
         for f in self.dec_mod_ops:
             f()
@@ -531,7 +540,7 @@ class UNetEngine:
             raise ops._lib.AsyrpError("UNetEngine needs a CUDA device (sm_100a); there is no CPU path")
         ops._lib.load()
         self.arch, self.device, self.n_delta = arch, torch.device(device), n_delta
-        self.state = {"ignore_timestep": False}
+        self.state = {"ignore_timestep": False, "slerp_t": 0.0, "use_mask": False}
         with torch.cuda.device(self.device):
             self.W, self.emb_off, self.emb_total = pack_weights(arch, state_dict, self.device, n_delta)
         self.plans = {}
@@ -544,20 +553,29 @@ class UNetEngine:
         return self.plans[N]
 
     # ---- reference forward() semantics -------------------------------------------------------------
-    def forward(self, x, t, index=None, t_edit=400, hs_coeff=(1.0, 1.0), ignore_timestep=False):
-        """(et, et_modified | None, delta_h | None, middle_h) as fp32 NCHW tensors (new tensors, like the reference)."""
+    def forward(self, x, t, index=None, t_edit=400, hs_coeff=(1.0, 1.0), ignore_timestep=False, delta_h=None,
+                use_mask=False):
+        """(et, et_modified | None, delta_h | None, middle_h) as fp32 NCHW tensors (new tensors, like the reference).
+        delta_h given: the explicit-Δh branch, h2 = slerp(1 - hs_coeff[0], h, |h| Δh / |Δh|) (ddpm/diffusion.py:518-539)."""
         N = x.shape[0]
         P = self.plan(N)
         with torch.cuda.device(self.device):
             P.x.copy_(x)
             P.t.copy_(t.to(torch.float32))
             edit = index is not None and float(t[0]) >= t_edit  # host decision, ddpm/diffusion.py:510
-            if index is not None and index + 1 > self.n_delta and edit:
+            explicit = delta_h is not None
+            if index is not None and index + 1 > self.n_delta and edit and not explicit:
                 raise ops._lib.AsyrpError(f"index={index} needs {index + 1} DeltaBlocks; engine packed {self.n_delta}")
             self.state["ignore_timestep"] = bool(ignore_timestep)
             P.run_encoder()
             delta = None
-            if edit:
+            if edit and explicit:
+                dh = delta_h.detach().to(self.device, torch.float32)
+                P.dh_user.copy_(dh if dh.dim() == 4 else dh[None].expand_as(P.dh_user))
+                self.state["slerp_t"], self.state["use_mask"] = 1.0 - float(hs_coeff[0]), bool(use_mask)
+                P.run_edit(explicit=True)
+                delta = delta_h  # the reference returns the tensor it was given
+            elif edit:
                 if index + 1 != self.n_delta:
                     raise ops._lib.AsyrpError("forward(index=i) requires i+1 == number of packed DeltaBlocks")
                 P.set_coeffs(hs_coeff)
@@ -573,6 +591,8 @@ class UNetEngine:
                 et_mod = P.et_mod.clone()
             else:
                 et_mod = et.clone()  # h2 = h below t_edit: the reference's second decoder pass is bit-identical
+                if explicit:
+                    delta = delta_h
             return et, et_mod, delta, P.mid_f32.clone()
 
     # ---- whole trajectory --------------------------------------------------------------------------

@@ -107,14 +107,11 @@ class _EngineUNet(nn.Module):
         return self._engine
 
     def _forward(self, x, t, index, t_edit, hs_coeff, delta_h, ignore_timestep, use_mask):
-        if delta_h is not None:
-            raise NotImplementedError("explicit delta_h (DiffStyle / slerp branch, ddpm/diffusion.py:518-539) is not "
-                                      "built yet; the DeltaBlock path (delta_h=None) is")
         eng = self.engine
         if not isinstance(hs_coeff, (tuple, list)):
             hs_coeff = (hs_coeff,)
         return eng.forward(x.to(eng.device), t.to(eng.device), index=index, t_edit=t_edit, hs_coeff=hs_coeff,
-                           ignore_timestep=ignore_timestep)
+                           ignore_timestep=ignore_timestep, delta_h=delta_h, use_mask=use_mask)
 
 
 class DDPM(_EngineUNet):

@@ -99,7 +99,7 @@ def f_img(key, steps, n_edit):
     return (steps * (e + d) + n_edit * (d + dl)) * 1e9
 
 
-def cpu_leg(family, key, traj_steps, n_edit, iters=1):
+def cpu_leg(family, key, traj_steps, n_edit, iters=1, threads=None):
     """time the CPU restatement of the reference (oracle/) on a bounded sample: B=1, one edit step (t=999) and one
     non-edit step (t=300, index=0 -> the reference still runs both decoders), scaled to the full trajectory"""
     from oracle import adm as oa, ddpm as od, sampler as osmp  # checker / baseline only
@@ -119,7 +119,7 @@ def cpu_leg(family, key, traj_steps, n_edit, iters=1):
     best_e, best_p, best_thr = float("inf"), float("inf"), os.cpu_count()
     # torch's CPU conv does not always scale to every core of a large host: time with all cores and with 32 threads,
     # report the faster (threads used are stated)
-    for thr in sorted({os.cpu_count(), min(32, os.cpu_count())}):
+    for thr in ([threads] if threads else sorted({os.cpu_count(), min(32, os.cpu_count())})):
       torch.set_num_threads(thr)
       for _ in range(iters):
         t0 = time.perf_counter()
@@ -172,11 +172,12 @@ def main():
         if rank != 0:
             return
         t0 = time.perf_counter()
+        # warm-up leg: also picks the faster of {all cores, 32 threads}; timed legs reuse that thread count
+        cb, _ = cpu_leg(family, key, traj_steps, sch.n_edit)
         vals = []
-        for _ in range(max(1, args.warmup > 0) + args.steps):
-            cb, traj_s = cpu_leg(family, key, traj_steps, sch.n_edit)
-            vals.append(cb)
-        cb = max(vals[1:] or vals, key=lambda c: c["value"])
+        for _ in range(args.steps):
+            vals.append(cpu_leg(family, key, traj_steps, sch.n_edit, threads=cb["cores"])[0])
+        cb = max(vals or [cb], key=lambda c: c["value"])
         line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "img/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / cb["value"],
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",

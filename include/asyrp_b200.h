@@ -122,6 +122,13 @@ int asyrp_ddim_update(const float* x, const float* et, const float* em, const fl
 /* out = alpha*a + beta*b, fp16 tensors of `numel` elements (multiple of 8) */
 int asyrp_axpby(const void* a, const void* b, void* out, float alpha, float beta, long long numel, void* stream);
 
+/* Explicit delta_h injection: h2 = slerp(t, h, |h|*dh/|dh|) per sample over C*H*W (models/ddpm/diffusion.py:6-40,
+ * 528-539; improved_ddpm/unet.py:720-730); use_mask: interpolate only rows 4..H-2 x columns 3..4 without norm
+ * matching, keep h elsewhere (:519-527).  h, h2: fp16 NHWC; dh: fp32 [C][H][W] per sample (stride 0 = shared).
+ * stats: [N][stats_tiles][C/2][2] partial sums of h2 (slot 0 filled, the others zeroed). */
+int asyrp_slerp_h(const void* h, const float* dh, long long dh_sample_stride, void* h2, float* stats, int stats_tiles,
+                  int N, int C, int H, int W, float t, int use_mask, void* stream);
+
 /* NHWC fp16 [N][HW][C] -> NCHW fp32 (API-visible delta_h / middle_h) */
 int asyrp_unpack_nchw(const void* in, float* out, int N, int C, int HW, void* stream);
 
