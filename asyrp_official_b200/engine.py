@@ -491,6 +491,8 @@ class Plan:
 
     # ------------------------------------------------------------------ execution
     def set_coeffs(self, hs_coeff):
+        if len(hs_coeff) < len(self.scale_ops) + 1:
+            return  # schedules without edit steps (origin pass, inversion) carry no DeltaBlock coefficients
         for op, i in self.scale_ops:
             op.set_scales(float(hs_coeff[i + 1]), float(hs_coeff[0]) if i == 0 else 1.0)
 
