@@ -256,6 +256,9 @@ def main():
            "api": "Asyrp.edit_batch(model, x_T pinned host, schedule, out=pinned host)"}
 
     if rank != 0:
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
         return
     # ---- per-kernel roofline of the dominant kernel (tcgen05 implicit-GEMM conv), per-launch CUDA events
     peak_tf, peak_gbs, peak_src = peaks()
@@ -290,6 +293,9 @@ def main():
             "Gaussian x_T)", "config": config, "roofline": roofline, "cpu_baseline": cb, "e2e": e2e,
             "gpu_launches": launches, "clocks": sampler.summary()}
     print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
