@@ -277,7 +277,11 @@ def main():
                 "gbs": round(d[2] / (d[0] * 1e-3) / 1e9, 1) if d[2] else None} for k, d in by.items()}
     roofline = {"bound": "tensor", "kernel": "conv_gemm_kernel (tcgen05 implicit GEMM, fp16 operands, fp32 accumulate)",
                 "achieved": round(conv_tf, 1), "peak": peak_tf, "unit": "TFLOP/s", "frac": round(conv_tf / peak_tf, 4),
-                "traffic": None, "peak_source": peak_src,
+                # ncu --set full, 128->128 @256x256 launch of the same build (profiles/r1_final_conv_ncu_full.csv):
+                # dram__bytes_read.sum + dram__bytes_write.sum per launch, vs 537 MB algorithmic
+                "traffic": {"bytes": 495.1e6, "algorithmic_bytes": 536.9e6, "launch": "3x3 128->128 @256x256, batch 16",
+                            "source": "profiles/r1_final_conv_ncu_full.csv"},
+                "peak_source": peak_src,
                 "how": f"sum of algorithmic conv FLOPs / sum of per-launch CUDA-event times over the {conv[3]} conv "
                        f"launches of one edit-step UNet evaluation (eager, same stream), batch {batch}",
                 "conv_share_of_step": round(conv[0] / tot_ms, 4),
