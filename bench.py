@@ -279,8 +279,9 @@ def main():
                 "achieved": round(conv_tf, 1), "peak": peak_tf, "unit": "TFLOP/s", "frac": round(conv_tf / peak_tf, 4),
                 # ncu --set full, 128->128 @256x256 launch of the same build (profiles/r1_final_conv_ncu_full.csv):
                 # dram__bytes_read.sum + dram__bytes_write.sum per launch, vs 537 MB algorithmic
-                "traffic": {"bytes": 495.1e6, "algorithmic_bytes": 536.9e6, "launch": "3x3 128->128 @256x256, batch 16",
-                            "source": "profiles/r1_final_conv_ncu_full.csv"},
+                "traffic": 495.1e6,
+                "traffic_note": "bytes per launch (dram read 268.8 MB + write 226.3 MB) of the 3x3 128->128 @256x256 "
+                                "batch-16 launch vs 536.9 MB algorithmic; profiles/r1_final_conv_ncu_full.csv",
                 "peak_source": peak_src,
                 "how": f"sum of algorithmic conv FLOPs / sum of per-launch CUDA-event times over the {conv[3]} conv "
                        f"launches of one edit-step UNet evaluation (eager, same stream), batch {batch}",
