@@ -14,7 +14,7 @@ c_void_p, c_int, c_float = C.c_void_p, C.c_int, C.c_float
 
 class AsyrpConvSeg(C.Structure):
     _fields_ = [("src", c_void_p), ("C", c_int), ("mode", c_int), ("affine", c_void_p), ("affine_stride", c_int),
-                ("act", c_int)]
+                ("act", c_int), ("ld", c_int)]
 
 
 class AsyrpConvDesc(C.Structure):
@@ -24,6 +24,8 @@ class AsyrpConvDesc(C.Structure):
         ("seg", AsyrpConvSeg * 3),
         ("weight", c_void_p),
         ("weight_batched", c_int),
+        ("weight_ld", c_int),
+        ("weight_batch_stride", C.c_longlong),
         ("ebias", c_void_p),
         ("ebias_stride", c_int),
         ("residual", c_void_p),
@@ -57,6 +59,8 @@ SIGNATURES = {
     "asyrp_unpack_nchw": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "asyrp_slerp_h": (c_int, [c_void_p, c_void_p, C.c_longlong, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                               c_float, c_int, c_void_p]),
+    "asyrp_transpose_tc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "asyrp_softmax_rows": (c_int, [c_void_p, c_void_p, C.c_longlong, c_int, c_float, c_void_p]),
     "asyrp_attention": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p]),
 }
 

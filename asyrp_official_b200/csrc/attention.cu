@@ -134,9 +134,74 @@ static int launch_attention(const void* qkv, void* out, int N, int T, int heads,
   return ASYRP_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Tensor-core attention helpers: the two GEMMs (q k^T, P v) run on conv_gemm_kernel in batched-weight mode;
+// these two kernels are the glue: v -> v^T (the P v GEMM wants K-major rows) and the fp32 row softmax.
+// ---------------------------------------------------------------------------------------------------------
+// in: [N][T][ld] (C channels from `in`), out: [N][C][T]
+__global__ void __launch_bounds__(256) transpose_tc_kernel(const __half* __restrict__ in, __half* __restrict__ out,
+                                                           int T, int C, int ld) {
+  __shared__ __half tile[32][34];
+  const int n = blockIdx.z, t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8)
+    if (t0 + i < T) tile[i][tx] = in[(static_cast<size_t>(n) * T + t0 + i) * ld + c0 + tx];
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8)
+    if (t0 + tx < T) out[(static_cast<size_t>(n) * C + c0 + i) * T + t0 + tx] = tile[tx][i];
+}
+
+// P[r][:] = softmax(scale * S[r][:]) over T columns, fp32 math (th.softmax(weight.float()), unet.py:393); one warp per row
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const __half* __restrict__ S, __half* __restrict__ P,
+                                                           int rows, int T, float scale) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const __half* s = S + static_cast<size_t>(row) * T;
+  __half* o = P + static_cast<size_t>(row) * T;
+  float v[32];  // T <= 1024
+  float mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const int c = lane + i * 32;
+    v[i] = c < T ? __half2float(s[c]) * scale : -INFINITY;
+    mx = fmaxf(mx, v[i]);
+  }
+  for (int of = 16; of > 0; of >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, of));
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    v[i] = __expf(v[i] - mx);
+    sum += v[i];
+  }
+  for (int of = 16; of > 0; of >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, of);
+  const float inv = 1.0f / sum;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const int c = lane + i * 32;
+    if (c < T) o[c] = __float2half_rn(v[i] * inv);
+  }
+}
+
 }  // namespace asyrp
 
 using namespace asyrp;
+
+extern "C" ASYRP_API int asyrp_transpose_tc(const void* in, void* out, int N, int T, int C, int ld, void* stream) {
+  ASYRP_REQUIRE(C % 32 == 0, "asyrp_transpose_tc: C=%d must be a multiple of 32", C);
+  dim3 grid((T + 31) / 32, C / 32, N);
+  transpose_tc_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __half*>(in),
+                                                                           static_cast<__half*>(out), T, C, ld);
+  ASYRP_CHECK_CUDA(cudaGetLastError());
+  return ASYRP_OK;
+}
+
+extern "C" ASYRP_API int asyrp_softmax_rows(const void* S, void* P, long long rows, int T, float scale, void* stream) {
+  ASYRP_REQUIRE(T >= 1 && T <= 1024, "asyrp_softmax_rows: T=%d out of range (<= 1024)", T);
+  softmax_rows_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __half*>(S), static_cast<__half*>(P), static_cast<int>(rows), T, scale);
+  ASYRP_CHECK_CUDA(cudaGetLastError());
+  return ASYRP_OK;
+}
 
 extern "C" ASYRP_API int asyrp_attention(const void* qkv, void* out, int N, int T, int heads, int head_dim,
                                          float scale, void* stream) {

@@ -639,6 +639,7 @@ struct AsyrpConvSeg {
                         // affine + n*affine_stride floats; the operand becomes act(a*x + b)
   int affine_stride;
   int act;              // 1: SiLU
+  int ld;               // elements between consecutive pixels of `src` (0: C) — channel slices of a wider tensor
 };
 
 struct AsyrpConvDesc {
@@ -647,6 +648,8 @@ struct AsyrpConvDesc {
   AsyrpConvSeg seg[3];
   const void* weight;  // fp16 [batch?][Cout][Ktot]
   int weight_batched;  // 1: one weight matrix per sample (requires 128-row tiles within one sample)
+  int weight_ld;       // elements between consecutive weight rows (0: Ktot)
+  long long weight_batch_stride;  // elements between consecutive samples' matrices (0: Cout*weight_ld)
   const float* ebias;  // fp32, row n at ebias + n*ebias_stride (stride 0: shared row), or null
   int ebias_stride;
   const void* residual;  // fp16 NHWC [N][H][W][Cout] or null
@@ -770,10 +773,13 @@ ASYRP_API int asyrp_conv_create(const AsyrpConvDesc* d, void** out_op) {
     uint64_t dims[5], strides[4];
     uint32_t box[5];
     const uint64_t C = sg.C;
+    const uint64_t L = sg.ld > 0 ? sg.ld : sg.C;  // pixel pitch
+    ASYRP_REQUIRE(L >= C && L % 8 == 0, "asyrp_conv_create: segment ld=%d must be >= C and a multiple of 8", sg.ld);
+    ASYRP_REQUIRE(!(sg.mode == 2 && L != C), "asyrp_conv_create: stride-2 segments need a dense source");
     if (sg.mode != 2) {
       const uint64_t H = d->H, W = d->W;
       dims[0] = C; dims[1] = W; dims[2] = d->N; dims[3] = 1; dims[4] = H;
-      strides[0] = C * 2; strides[1] = H * W * C * 2; strides[2] = W * C * 2; strides[3] = W * C * 2;
+      strides[0] = L * 2; strides[1] = H * W * L * 2; strides[2] = W * L * 2; strides[3] = W * L * 2;
       box[0] = 64; box[1] = mode == 3 ? p.TW + 2 : p.TW; box[2] = p.NB; box[3] = 1;
       box[4] = (mode == 1 || mode == 3) ? THT + 2 : THT;
     } else {
@@ -789,7 +795,11 @@ ASYRP_API int asyrp_conv_create(const AsyrpConvDesc* d, void** out_op) {
   {
     uint64_t dims[3] = {static_cast<uint64_t>(ktot), static_cast<uint64_t>(d->Cout),
                         static_cast<uint64_t>(d->weight_batched ? d->N : 1)};
-    uint64_t strides[2] = {static_cast<uint64_t>(ktot) * 2, static_cast<uint64_t>(ktot) * d->Cout * 2};
+    const uint64_t wld = d->weight_ld > 0 ? d->weight_ld : ktot;
+    const uint64_t wbs = d->weight_batch_stride > 0 ? static_cast<uint64_t>(d->weight_batch_stride) : wld * d->Cout;
+    ASYRP_REQUIRE(wld >= static_cast<uint64_t>(ktot) && wld % 8 == 0 && wbs % 8 == 0,
+                  "asyrp_conv_create: weight_ld / weight_batch_stride must cover K and be multiples of 8");
+    uint64_t strides[2] = {wld * 2, wbs * 2};
     uint32_t box[3] = {64, static_cast<uint32_t>(op->BN), 1};
     int rc = encode_tensor_map(&p.tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, d->weight, dims, strides, box,
                                CU_TENSOR_MAP_SWIZZLE_128B);

@@ -349,8 +349,24 @@ class Plan:
         att = self._act(x.H, x.W, C, stats=False)
         N, T = self.N, x.H * x.W
         scale = float(d) ** -0.5  # C^-0.5 (ddpm/diffusion.py:213) == (d^-1/4)^2 (improved_ddpm/unet.py:389-392)
-        self._emit(lambda: ops.attention(qkv.t.view(N, T, 3 * C), att.t.view(N, T, C), heads, d, scale), "attention",
-                   flops=4.0 * N * T * T * C, nbytes=2.0 * N * T * 4 * C)
+        if heads == 1 and T % 128 == 0 and T <= 1024:
+            # tensor-core path: S = q k^T and O = P v are batched GEMMs on the conv kernel (per-sample "weights" k / v^T)
+            qkv3 = qkv.t.view(N, T, 3 * C)
+            q4 = qkv.t.view(N, 1, T, 3 * C)[..., :C]
+            S = self.pool.alloc((N, 1, T, T), torch.float16)
+            Pm = self.pool.alloc((N, 1, T, T), torch.float16)
+            vT = self.pool.alloc((N, C, T), torch.float16)
+            op_s = ops.ConvOp([(q4, MODE_1x1)], qkv3[:, :, C:2 * C], out=S, weight_batched=True)
+            self._emit(op_s.launch, "attention", flops=2.0 * N * T * T * C)
+            self._emit(lambda: ops.transpose_tc(qkv3[:, :, 2 * C:], vT), "attention")
+            self._emit(lambda: ops.softmax_rows(S, Pm, scale), "attention")
+            op_o = ops.ConvOp([(Pm, MODE_1x1)], vT, out=att.t.view(N, 1, T, C), weight_batched=True)
+            self._emit(op_o.launch, "attention", flops=2.0 * N * T * T * C)
+            for buf in (S, Pm, vT):
+                self.pool.release(buf)
+        else:
+            self._emit(lambda: ops.attention(qkv.t.view(N, T, 3 * C), att.t.view(N, T, C), heads, d, scale),
+                       "attention", flops=4.0 * N * T * T * C, nbytes=2.0 * N * T * 4 * C)
         out, _ = self._conv([(att, MODE_1x1)], W[p + ".wproj"], C, x.H, x.W, ebias=W[p + ".bproj"], residual=x)
         self._free(qkv)
         self._free(att)

@@ -74,21 +74,28 @@ class ConvOp:
         d.nseg = len(segs)
         ktot = 0
         for i, (src, mode, aff, aff_off, act) in enumerate(segs):
-            assert src.dtype == torch.float16 and src.is_contiguous()
+            # dense NHWC, or a channel slice of a dense NHWC tensor (pixel pitch ld = stride of the W axis)
+            n_, h_, w_, c_ = src.shape
+            ld = src.stride(2)
+            assert src.dtype == torch.float16 and src.stride(3) == 1 and src.stride(1) == w_ * ld \
+                and (n_ == 1 or src.stride(0) == h_ * w_ * ld), src.stride()
             d.seg[i].src = src.data_ptr()
             d.seg[i].C = src.shape[-1]
             d.seg[i].mode = mode
+            d.seg[i].ld = ld
             if aff is not None:
                 assert aff.dtype == torch.float32 and aff.is_contiguous() and aff.shape[-1] == 2
                 d.seg[i].affine = aff.data_ptr() + aff_off * 2 * 4
                 d.seg[i].affine_stride = aff.shape[1] * 2
                 d.seg[i].act = int(act)
             ktot += (1 if mode == MODE_1x1 else 9) * src.shape[-1]
-        assert weight.dtype == torch.float16 and weight.is_contiguous() and weight.shape[-1] == ktot, \
-            (weight.shape, ktot)
+        assert weight.dtype == torch.float16 and weight.stride(-1) == 1 and weight.shape[-1] == ktot, \
+            (weight.shape, weight.stride(), ktot)
         assert weight.shape[-2] == Cout
         d.weight = weight.data_ptr()
         d.weight_batched = int(weight_batched)
+        d.weight_ld = weight.stride(-2)
+        d.weight_batch_stride = weight.stride(0) if (weight_batched and weight.dim() == 3) else 0
         d.ebias = ebias.data_ptr() if ebias is not None else None
         d.ebias_stride = ebias_stride
         d.residual = residual.data_ptr() if residual is not None else None
@@ -195,3 +202,16 @@ def slerp_h(h, dh, h2, stats, t, use_mask=False):
     stride = dh.stride(0) if dh.dim() == 4 else 0
     check(lib.asyrp_slerp_h(_ptr(h), _ptr(dh), stride, _ptr(h2), _ptr(stats), stats.shape[1], N, Cc, H, W, float(t),
                             int(use_mask), _stream()), "asyrp_slerp_h")
+
+
+def transpose_tc(inp, out):
+    """inp [N][T][C] (may be a channel slice: last-dim stride 1, row stride ld) -> out [N][C][T] fp16"""
+    lib = _lib.load()
+    N, T, Cc = inp.shape
+    check(lib.asyrp_transpose_tc(_ptr(inp), _ptr(out), N, T, Cc, inp.stride(1), _stream()), "asyrp_transpose_tc")
+
+
+def softmax_rows(S, P, scale):
+    lib = _lib.load()
+    T = S.shape[-1]
+    check(lib.asyrp_softmax_rows(_ptr(S), _ptr(P), S.numel() // T, T, float(scale), _stream()), "asyrp_softmax_rows")

@@ -56,6 +56,8 @@ typedef struct AsyrpConvSeg {
   const float* affine;
   int affine_stride;
   int act;         /* 1: SiLU after the affine */
+  int ld;          /* elements between consecutive pixels of src (0: C): lets a segment be a channel slice of a wider
+                      tensor, e.g. q = qkv[..., 0:C] */
 } AsyrpConvSeg;
 
 typedef struct AsyrpConvDesc {
@@ -64,6 +66,8 @@ typedef struct AsyrpConvDesc {
   AsyrpConvSeg seg[3];
   const void* weight;    /* fp16 [Cout][K] ([N][Cout][K] if weight_batched), K = sum_seg taps*C */
   int weight_batched;    /* per-sample weight matrix (batched GEMM, e.g. q k^T) */
+  int weight_ld;         /* elements between weight rows (0: K) */
+  long long weight_batch_stride; /* elements between per-sample matrices (0: Cout*weight_ld) */
   const float* ebias;    /* fp32 bias row(s): row n at ebias + n*ebias_stride; NULL = none */
   int ebias_stride;      /* 0: one row shared by all samples (plain bias);
                             >0: per-sample rows (conv bias + timestep-embedding projection) */
@@ -136,6 +140,12 @@ int asyrp_unpack_nchw(const void* in, float* out, int N, int C, int HW, void* st
  * h*head_dim; out fp16 [N][T][heads*head_dim].  Replaces the bmm/softmax/bmm of AttnBlock.forward
  * (ddpm/diffusion.py:206-221) and QKVAttentionLegacy.forward (improved_ddpm/unet.py:379-396). */
 int asyrp_attention(const void* qkv, void* out, int N, int T, int heads, int head_dim, float scale, void* stream);
+
+/* Tensor-core attention glue (single-head blocks with T >= 128: the q k^T and P v GEMMs run on the conv kernel with
+ * weight_batched = 1).  asyrp_transpose_tc: [N][T][ld] (first C channels at `in`) -> [N][C][T].
+ * asyrp_softmax_rows: P = softmax(scale * S) per row of T <= 1024 fp16 values, fp32 math. */
+int asyrp_transpose_tc(const void* in, void* out, int N, int T, int C, int ld, void* stream);
+int asyrp_softmax_rows(const void* S, void* P, long long rows, int T, float scale, void* stream);
 
 #ifdef __cplusplus
 }

@@ -357,3 +357,34 @@ def test_fused_operand_planar_output(cuda_device):
     op.launch()
     torch.cuda.synchronize()
     _check(outp.cpu(), ref, 2.5e-3, "fused planar")
+
+
+def test_tensor_core_attention_pieces(cuda_device):
+    """q k^T and P v as batched GEMMs on channel slices of one qkv tensor (pixel pitch 3C), v -> v^T, row softmax:
+    the single-head attention path of AttnBlock (ddpm/diffusion.py:200-221) on tensor cores"""
+    ops = _ops()
+    g = torch.Generator().manual_seed(21)
+    N, T, Cc = 3, 256, 128
+    qkv = _rand((N, T, 3 * Cc), g).to(torch.float16)
+    qd = qkv.to(cuda_device)
+    q, k, v = (qkv[..., i * Cc:(i + 1) * Cc].double() for i in range(3))
+    S = torch.empty(N, 1, T, T, dtype=torch.float16, device=cuda_device)
+    ops.ConvOp([(qd.view(N, 1, T, 3 * Cc)[..., :Cc], ops.MODE_1x1)], qd[:, :, Cc:2 * Cc], out=S, weight_batched=True).launch()
+    s_ref = torch.einsum("ntc,nsc->nts", q, k)
+    torch.cuda.synchronize()
+    _check(S.float().cpu().reshape(N, T, T), s_ref, 1.5e-3, "q k^T on slices")
+    P = torch.empty_like(S)
+    scale = Cc ** -0.5
+    ops.softmax_rows(S, P, scale)
+    p_ref = torch.softmax(S.double().cpu().reshape(N, T, T) * scale, dim=-1)
+    torch.cuda.synchronize()
+    assert (P.double().cpu().reshape(N, T, T) - p_ref).abs().max().item() < 6e-4
+    vT = torch.empty(N, Cc, T, dtype=torch.float16, device=cuda_device)
+    ops.transpose_tc(qd[:, :, 2 * Cc:], vT)
+    torch.cuda.synchronize()
+    assert torch.equal(vT.cpu(), qkv[..., 2 * Cc:].transpose(1, 2).contiguous())
+    O = torch.empty(N, 1, T, Cc, dtype=torch.float16, device=cuda_device)
+    ops.ConvOp([(P, ops.MODE_1x1)], vT, out=O, weight_batched=True).launch()
+    torch.cuda.synchronize()
+    o_ref = torch.einsum("nts,nsc->ntc", P.double().cpu().reshape(N, T, T), v)
+    _check(O.float().cpu().reshape(N, T, Cc), o_ref, 1.5e-3, "P v")
