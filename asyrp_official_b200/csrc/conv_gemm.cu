@@ -68,6 +68,11 @@ struct ConvParams {
   int planar_c;
   float* stats;            // [N][tiles_y*tiles_x][Cout/2][2] partial (sum, sumsq) or nullptr
   int b_batched;           // weights have a per-sample batch dimension (attention GEMMs)
+  // multi-head attention GEMMs: the batch index ns of a tile is (sample, head).  a_heads > 1: the activation map has
+  // a head dimension (64-channel slices of one tensor); b_heads likewise for the per-sample weights; out_heads > 1:
+  // the Cout columns of batch entry ns = n*out_heads + head go to channels [head*Cout, (head+1)*Cout) of sample n
+  int a_heads, b_heads, out_heads;
+  int out_ld;              // elements between consecutive output pixels (Cout * out_heads)
   int any_transform;       // some segment has an affine: the MMA warp then waits on readyA instead of fullA
 };
 
@@ -158,7 +163,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
               if (sg.mode == 3) {
                 tma_load_5d(dst, &p.tmA[s], &fullA[sa], ch * 64, x0 - 1, n0, 0, y0 - 1);
               } else if (sg.mode == 0) {
-                tma_load_5d(dst, &p.tmA[s], &fullA[sa], ch * 64, x0, n0, 0, y0);
+                tma_load_5d(dst, &p.tmA[s], &fullA[sa], ch * 64, x0, n0 / p.a_heads, n0 % p.a_heads, y0);
               } else if (sg.mode == 1) {
                 tma_load_5d(dst, &p.tmA[s], &fullA[sa], ch * 64, x0 + cp - 1, n0, 0, y0 - 1);
               } else {
@@ -181,6 +186,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
         const int mt = tile % p.m_tiles, nt = tile / p.m_tiles;
         const int tn = mt / (p.tiles_x * p.tiles_y);
         const int bz = p.b_batched ? tn * p.NB : 0;
+        const int b_n = bz / p.b_heads, b_h = bz % p.b_heads;
         for (int s = 0; s < p.nseg; ++s) {
           const ConvSegDev sg = p.seg[s];
           const int ncopies = (sg.mode == 0 || sg.mode == 3) ? 1 : (sg.mode == 1 ? 3 : 9);
@@ -192,7 +198,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
                 const int tap = sg.mode == 0 ? 0 : (sg.mode == 1 ? tp * 3 + cp : (sg.mode == 3 ? tp : cp));
                 mbar_wait(&emptyB[sb], pb ^ 1);
                 mbar_arrive_expect_tx(&fullB[sb], kBStage);
-                tma_load_3d(sB + sb * kBStage, &p.tmB, &fullB[sb], sg.kbase + tap * sg.C + ch * 64, nt * BN, bz);
+                tma_load_4d(sB + sb * kBStage, &p.tmB, &fullB[sb], sg.kbase + tap * sg.C + ch * 64, nt * BN, b_h, b_n);
                 if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
               }
             }
@@ -470,7 +476,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
         for (int sub = 0; sub < MT; ++sub) {
           const int y = ty * THT + sub * p.TH + yy;
           const bool valid = (x < p.W) && (y < p.H) && (n < p.N);
-          const size_t pix = (static_cast<size_t>(n) * p.H + y) * p.W + x;
+          // output row of this pixel: batch entry n may be a (sample, head) pair writing a channel slice
+          const size_t pix = ((static_cast<size_t>(n / p.out_heads) * p.H + y) * p.W + x) * p.out_ld +
+                             static_cast<size_t>(n % p.out_heads) * p.Cout;
           uint32_t r[32];
           tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * (MT * BN) + sub * BN + cc * 32, r);
           tmem_ld_wait();
@@ -490,7 +498,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
             for (int i = 0; i < 32; ++i) v[i] *= p.acc_scale;
           }
           if (p.res != nullptr && valid) {
-            const uint4* rp = reinterpret_cast<const uint4*>(p.res + pix * p.Cout + c0);
+            const uint4* rp = reinterpret_cast<const uint4*>(p.res + pix + c0);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const uint4 u = rp[j];
@@ -512,7 +520,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
                 if (i < p.planar_c) pp[i * hw] = v[i];
             }
           } else if (valid) {
-            uint4* op = reinterpret_cast<uint4*>(p.out + pix * p.Cout + c0);
+            uint4* op = reinterpret_cast<uint4*>(p.out + pix + c0);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               uint4 u;
@@ -650,6 +658,10 @@ struct AsyrpConvDesc {
   int weight_batched;  // 1: one weight matrix per sample (requires 128-row tiles within one sample)
   int weight_ld;       // elements between consecutive weight rows (0: Ktot)
   long long weight_batch_stride;  // elements between consecutive samples' matrices (0: Cout*weight_ld)
+  // multi-head batched GEMMs (attention): N counts (sample, head) pairs
+  int a_heads;         // >1: segment 0 is [N/a_heads][H][W][ld] and head h reads channels [h*C, (h+1)*C)
+  int b_heads;         // >1: the weights are [N/b_heads][Cout][weight_ld] and head h reads columns [h*K, (h+1)*K)
+  int out_heads;       // >1: out is [N/out_heads][H][W][out_heads*Cout], head h writes channels [h*Cout, ...)
   const float* ebias;  // fp32, row n at ebias + n*ebias_stride (stride 0: shared row), or null
   int ebias_stride;
   const void* residual;  // fp16 NHWC [N][H][W][Cout] or null
@@ -778,8 +790,11 @@ ASYRP_API int asyrp_conv_create(const AsyrpConvDesc* d, void** out_op) {
     ASYRP_REQUIRE(!(sg.mode == 2 && L != C), "asyrp_conv_create: stride-2 segments need a dense source");
     if (sg.mode != 2) {
       const uint64_t H = d->H, W = d->W;
-      dims[0] = C; dims[1] = W; dims[2] = d->N; dims[3] = 1; dims[4] = H;
-      strides[0] = L * 2; strides[1] = H * W * L * 2; strides[2] = W * L * 2; strides[3] = W * L * 2;
+      const uint64_t ah = (s == 0 && d->a_heads > 1) ? d->a_heads : 1;
+      ASYRP_REQUIRE(ah == 1 || (sg.mode == 0 && d->nseg == 1 && d->N % ah == 0 && L >= ah * C),
+                    "asyrp_conv_create: a_heads needs one 1x1 segment with ld >= heads*C");
+      dims[0] = C; dims[1] = W; dims[2] = d->N / ah; dims[3] = ah; dims[4] = H;
+      strides[0] = L * 2; strides[1] = H * W * L * 2; strides[2] = (ah > 1 ? C : W * L) * 2; strides[3] = W * L * 2;
       box[0] = 64; box[1] = mode == 3 ? p.TW + 2 : p.TW; box[2] = p.NB; box[3] = 1;
       box[4] = (mode == 1 || mode == 3) ? THT + 2 : THT;
     } else {
@@ -793,19 +808,29 @@ ASYRP_API int asyrp_conv_create(const AsyrpConvDesc* d, void** out_op) {
     if (rc != ASYRP_OK) { delete op; return rc; }
   }
   {
-    uint64_t dims[3] = {static_cast<uint64_t>(ktot), static_cast<uint64_t>(d->Cout),
-                        static_cast<uint64_t>(d->weight_batched ? d->N : 1)};
+    const uint64_t bh = (d->weight_batched && d->b_heads > 1) ? d->b_heads : 1;
+    uint64_t dims[4] = {static_cast<uint64_t>(ktot), static_cast<uint64_t>(d->Cout), bh,
+                        static_cast<uint64_t>(d->weight_batched ? d->N / bh : 1)};
     const uint64_t wld = d->weight_ld > 0 ? d->weight_ld : ktot;
     const uint64_t wbs = d->weight_batch_stride > 0 ? static_cast<uint64_t>(d->weight_batch_stride) : wld * d->Cout;
     ASYRP_REQUIRE(wld >= static_cast<uint64_t>(ktot) && wld % 8 == 0 && wbs % 8 == 0,
                   "asyrp_conv_create: weight_ld / weight_batch_stride must cover K and be multiples of 8");
-    uint64_t strides[2] = {wld * 2, wbs * 2};
-    uint32_t box[3] = {64, static_cast<uint32_t>(op->BN), 1};
-    int rc = encode_tensor_map(&p.tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, d->weight, dims, strides, box,
+    ASYRP_REQUIRE(bh == 1 || wld >= bh * static_cast<uint64_t>(ktot), "asyrp_conv_create: b_heads needs weight_ld >= heads*K");
+    // dim 2 = head (column slices of width K inside a row of weight_ld elements), dim 3 = sample
+    uint64_t strides[3] = {wld * 2, (bh > 1 ? static_cast<uint64_t>(ktot) : wbs) * 2, wbs * 2};
+    uint32_t box[4] = {64, static_cast<uint32_t>(op->BN), 1, 1};
+    int rc = encode_tensor_map(&p.tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, d->weight, dims, strides, box,
                                CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != ASYRP_OK) { delete op; return rc; }
   }
   p.b_batched = d->weight_batched;
+  p.a_heads = d->a_heads > 1 ? d->a_heads : 1;
+  p.b_heads = (d->weight_batched && d->b_heads > 1) ? d->b_heads : 1;
+  p.out_heads = d->out_heads > 1 ? d->out_heads : 1;
+  p.out_ld = d->Cout * p.out_heads;
+  ASYRP_REQUIRE(p.out_heads == 1 || (d->N % p.out_heads == 0 && d->stats == nullptr && d->out_planar == nullptr &&
+                                     !(op->BN == 128 && op->MT == 2)),
+                "asyrp_conv_create: out_heads needs N %% heads == 0, no stats / planar output, Cout != 128*odd");
   p.a_stage_bytes = halo ? (((THT + 2) * (p.TW + 2) * 128u + 1023u) / 1024u) * 1024u
                          : (any3 ? THT + 2 : THT) * p.row_bytes;
   const uint32_t b_stage = op->BN * 128;

@@ -364,6 +364,24 @@ class Plan:
             self._emit(op_o.launch, "attention", flops=2.0 * N * T * T * C)
             for buf in (S, Pm, vT):
                 self.pool.release(buf)
+        elif d == 64 and T % 128 == 0 and T <= 1024:
+            # multi-head (QKVAttentionLegacy): the same two GEMMs batched over (sample, head); q_h / k_h are 64-channel
+            # slices of the qkv tensor (head dimension in the TMA maps), O_h is written into its channel slice
+            qkv3 = qkv.t.view(N, T, 3 * C)
+            q4 = qkv.t.view(N, 1, T, 3 * C)[..., :d]
+            S = self.pool.alloc((N * heads, 1, T, T), torch.float16)
+            Pm = self.pool.alloc((N * heads, 1, T, T), torch.float16)
+            vT = self.pool.alloc((N, C, T), torch.float16)
+            op_s = ops.ConvOp([(q4, MODE_1x1)], qkv3[:, :, C:C + d], out=S, weight_batched=True, a_heads=heads,
+                              b_heads=heads)
+            self._emit(op_s.launch, "attention", flops=2.0 * N * T * T * C)
+            self._emit(lambda: ops.transpose_tc(qkv3[:, :, 2 * C:], vT), "attention")
+            self._emit(lambda: ops.softmax_rows(S, Pm, scale), "attention")
+            op_o = ops.ConvOp([(Pm, MODE_1x1)], vT.view(N * heads, d, T), out=att.t.view(N, 1, T, C),
+                              weight_batched=True, out_heads=heads)
+            self._emit(op_o.launch, "attention", flops=2.0 * N * T * T * C)
+            for buf in (S, Pm, vT):
+                self.pool.release(buf)
         else:
             self._emit(lambda: ops.attention(qkv.t.view(N, T, 3 * C), att.t.view(N, T, C), heads, d, scale),
                        "attention", flops=4.0 * N * T * T * C, nbytes=2.0 * N * T * 4 * C)

@@ -59,7 +59,8 @@ class ConvOp:
     """
 
     def __init__(self, segs, weight, out=None, ebias=None, ebias_stride=0, residual=None, res_scale=1.0,
-                 acc_scale=1.0, stats=None, out_planar=None, out_shape=None, weight_batched=False):
+                 acc_scale=1.0, stats=None, out_planar=None, out_shape=None, weight_batched=False, a_heads=1,
+                 b_heads=1, out_heads=1):
         lib = _lib.load()
         segs = [tuple(sg) + (None, 0, 0) * (len(sg) == 2) for sg in segs]
         srcs = [sg[0] for sg in segs]
@@ -67,6 +68,8 @@ class ConvOp:
         _need_cuda(*srcs, *affs, weight, out, ebias, residual, stats, out_planar)
         if out is not None:
             N, H, W, Cout = out.shape
+            if out_heads > 1:  # out [n][H][W][heads*Cout] receives batch entries (n, head)
+                N, Cout = N * out_heads, Cout // out_heads
         else:
             N, H, W, Cout = out_shape
         d = AsyrpConvDesc()
@@ -96,6 +99,7 @@ class ConvOp:
         d.weight_batched = int(weight_batched)
         d.weight_ld = weight.stride(-2)
         d.weight_batch_stride = weight.stride(0) if (weight_batched and weight.dim() == 3) else 0
+        d.a_heads, d.b_heads, d.out_heads = a_heads, b_heads, out_heads
         d.ebias = ebias.data_ptr() if ebias is not None else None
         d.ebias_stride = ebias_stride
         d.residual = residual.data_ptr() if residual is not None else None

@@ -68,6 +68,11 @@ typedef struct AsyrpConvDesc {
   int weight_batched;    /* per-sample weight matrix (batched GEMM, e.g. q k^T) */
   int weight_ld;         /* elements between weight rows (0: K) */
   long long weight_batch_stride; /* elements between per-sample matrices (0: Cout*weight_ld) */
+  /* multi-head attention GEMMs (QKVAttentionLegacy, improved_ddpm/unet.py:379-396): N counts (sample, head) pairs.
+   * a_heads > 1: segment 0 is [N/a_heads][H][W][ld], head h reads channels [h*C, (h+1)*C);
+   * b_heads > 1: weights are [N/b_heads][Cout][weight_ld], head h reads columns [h*K, (h+1)*K);
+   * out_heads > 1: out is [N/out_heads][H][W][out_heads*Cout], head h writes channels [h*Cout, (h+1)*Cout). */
+  int a_heads, b_heads, out_heads;
   const float* ebias;    /* fp32 bias row(s): row n at ebias + n*ebias_stride; NULL = none */
   int ebias_stride;      /* 0: one row shared by all samples (plain bias);
                             >0: per-sample rows (conv bias + timestep-embedding projection) */

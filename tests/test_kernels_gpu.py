@@ -388,3 +388,29 @@ def test_tensor_core_attention_pieces(cuda_device):
     torch.cuda.synchronize()
     o_ref = torch.einsum("nts,nsc->ntc", P.double().cpu().reshape(N, T, T), v)
     _check(O.float().cpu().reshape(N, T, Cc), o_ref, 1.5e-3, "P v")
+
+
+def test_multi_head_attention_gemms(cuda_device):
+    """QKVAttentionLegacy (improved_ddpm/unet.py:379-396) on tensor cores: S_h = q_h k_h^T and O_h = P_h v_h batched
+    over (sample, head), heads being 64-channel slices of one qkv tensor; O_h lands in its channel slice"""
+    ops = _ops()
+    g = torch.Generator().manual_seed(22)
+    N, T, heads, d = 2, 256, 4, 64
+    Cc = heads * d
+    qkv = _rand((N, T, 3 * Cc), g).to(torch.float16)
+    qd = qkv.to(cuda_device)
+    q, k, v = (qkv[..., i * Cc:(i + 1) * Cc].double().reshape(N, T, heads, d).permute(0, 2, 1, 3) for i in range(3))
+    S = torch.empty(N * heads, 1, T, T, dtype=torch.float16, device=cuda_device)
+    ops.ConvOp([(qd.view(N, 1, T, 3 * Cc)[..., :d], ops.MODE_1x1)], qd[:, :, Cc:Cc + d], out=S, weight_batched=True,
+               a_heads=heads, b_heads=heads).launch()
+    torch.cuda.synchronize()
+    _check(S.float().cpu().reshape(N, heads, T, T), q @ k.transpose(-1, -2), 1.5e-3, "multi-head q k^T")
+    P = torch.empty_like(S)
+    ops.softmax_rows(S, P, d ** -0.5)
+    vT = torch.empty(N, Cc, T, dtype=torch.float16, device=cuda_device)
+    ops.transpose_tc(qd[:, :, 2 * Cc:], vT)
+    O = torch.empty(N, 1, T, Cc, dtype=torch.float16, device=cuda_device)
+    ops.ConvOp([(P, ops.MODE_1x1)], vT.view(N * heads, d, T), out=O, weight_batched=True, out_heads=heads).launch()
+    torch.cuda.synchronize()
+    o_ref = (P.double().cpu().reshape(N, heads, T, T) @ v).permute(0, 2, 1, 3).reshape(N, T, Cc)
+    _check(O.float().cpu().reshape(N, T, Cc), o_ref, 1.5e-3, "multi-head P v")
