@@ -26,7 +26,7 @@ class AsyrpConvDesc(C.Structure):
         ("weight_batched", c_int),
         ("weight_ld", c_int),
         ("weight_batch_stride", C.c_longlong),
-        ("a_heads", c_int), ("b_heads", c_int), ("out_heads", c_int),
+        ("a_heads", c_int), ("b_heads", c_int), ("out_heads", c_int), ("out_f32", c_int),
         ("ebias", c_void_p),
         ("ebias_stride", c_int),
         ("residual", c_void_p),

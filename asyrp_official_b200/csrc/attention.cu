@@ -152,18 +152,18 @@ __global__ void __launch_bounds__(256) transpose_tc_kernel(const __half* __restr
 }
 
 // P[r][:] = softmax(scale * S[r][:]) over T columns, fp32 math (th.softmax(weight.float()), unet.py:393); one warp per row
-__global__ void __launch_bounds__(256) softmax_rows_kernel(const __half* __restrict__ S, __half* __restrict__ P,
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ S, __half* __restrict__ P,
                                                            int rows, int T, float scale) {
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= rows) return;
-  const __half* s = S + static_cast<size_t>(row) * T;
+  const float* s = S + static_cast<size_t>(row) * T;
   __half* o = P + static_cast<size_t>(row) * T;
   float v[32];  // T <= 1024
   float mx = -INFINITY;
 #pragma unroll
   for (int i = 0; i < 32; ++i) {
     const int c = lane + i * 32;
-    v[i] = c < T ? __half2float(s[c]) * scale : -INFINITY;
+    v[i] = c < T ? s[c] * scale : -INFINITY;
     mx = fmaxf(mx, v[i]);
   }
   for (int of = 16; of > 0; of >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, of));
@@ -198,7 +198,7 @@ extern "C" ASYRP_API int asyrp_transpose_tc(const void* in, void* out, int N, in
 extern "C" ASYRP_API int asyrp_softmax_rows(const void* S, void* P, long long rows, int T, float scale, void* stream) {
   ASYRP_REQUIRE(T >= 1 && T <= 1024, "asyrp_softmax_rows: T=%d out of range (<= 1024)", T);
   softmax_rows_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __half*>(S), static_cast<__half*>(P), static_cast<int>(rows), T, scale);
+      static_cast<const float*>(S), static_cast<__half*>(P), static_cast<int>(rows), T, scale);
   ASYRP_CHECK_CUDA(cudaGetLastError());
   return ASYRP_OK;
 }

@@ -73,6 +73,7 @@ struct ConvParams {
   // the Cout columns of batch entry ns = n*out_heads + head go to channels [head*Cout, (head+1)*Cout) of sample n
   int a_heads, b_heads, out_heads;
   int out_ld;              // elements between consecutive output pixels (Cout * out_heads)
+  int out_f32;             // `out` is fp32 (attention logits keep fp32 precision for the softmax)
   int any_transform;       // some segment has an affine: the MMA warp then waits on readyA instead of fullA
 };
 
@@ -519,6 +520,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
               for (int i = 0; i < 8; ++i)
                 if (i < p.planar_c) pp[i * hw] = v[i];
             }
+          } else if (p.out_f32) {
+            if (valid) {
+              float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + pix + c0);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
           } else if (valid) {
             uint4* op = reinterpret_cast<uint4*>(p.out + pix + c0);
 #pragma unroll
@@ -662,6 +669,7 @@ struct AsyrpConvDesc {
   int a_heads;         // >1: segment 0 is [N/a_heads][H][W][ld] and head h reads channels [h*C, (h+1)*C)
   int b_heads;         // >1: the weights are [N/b_heads][Cout][weight_ld] and head h reads columns [h*K, (h+1)*K)
   int out_heads;       // >1: out is [N/out_heads][H][W][out_heads*Cout], head h writes channels [h*Cout, ...)
+  int out_f32;         // 1: `out` is fp32 NHWC instead of fp16 (no residual / stats; not with Cout == 128*odd)
   const float* ebias;  // fp32, row n at ebias + n*ebias_stride (stride 0: shared row), or null
   int ebias_stride;
   const void* residual;  // fp16 NHWC [N][H][W][Cout] or null
@@ -828,6 +836,10 @@ ASYRP_API int asyrp_conv_create(const AsyrpConvDesc* d, void** out_op) {
   p.b_heads = (d->weight_batched && d->b_heads > 1) ? d->b_heads : 1;
   p.out_heads = d->out_heads > 1 ? d->out_heads : 1;
   p.out_ld = d->Cout * p.out_heads;
+  p.out_f32 = d->out_f32;
+  ASYRP_REQUIRE(!d->out_f32 || (d->residual == nullptr && d->stats == nullptr && d->out_planar == nullptr &&
+                                !(op->BN == 128 && op->MT == 2)),
+                "asyrp_conv_create: out_f32 excludes residual / stats / planar output and the swapped-operand tile");
   ASYRP_REQUIRE(p.out_heads == 1 || (d->N % p.out_heads == 0 && d->stats == nullptr && d->out_planar == nullptr &&
                                      !(op->BN == 128 && op->MT == 2)),
                 "asyrp_conv_create: out_heads needs N %% heads == 0, no stats / planar output, Cout != 128*odd");

@@ -353,7 +353,7 @@ class Plan:
             # tensor-core path: S = q k^T and O = P v are batched GEMMs on the conv kernel (per-sample "weights" k / v^T)
             qkv3 = qkv.t.view(N, T, 3 * C)
             q4 = qkv.t.view(N, 1, T, 3 * C)[..., :C]
-            S = self.pool.alloc((N, 1, T, T), torch.float16)
+            S = self.pool.alloc((N, 1, T, T), torch.float32)  # logits stay fp32 for the softmax
             Pm = self.pool.alloc((N, 1, T, T), torch.float16)
             vT = self.pool.alloc((N, C, T), torch.float16)
             op_s = ops.ConvOp([(q4, MODE_1x1)], qkv3[:, :, C:2 * C], out=S, weight_batched=True)
@@ -369,7 +369,7 @@ class Plan:
             # slices of the qkv tensor (head dimension in the TMA maps), O_h is written into its channel slice
             qkv3 = qkv.t.view(N, T, 3 * C)
             q4 = qkv.t.view(N, 1, T, 3 * C)[..., :d]
-            S = self.pool.alloc((N * heads, 1, T, T), torch.float16)
+            S = self.pool.alloc((N * heads, 1, T, T), torch.float32)
             Pm = self.pool.alloc((N * heads, 1, T, T), torch.float16)
             vT = self.pool.alloc((N, C, T), torch.float16)
             op_s = ops.ConvOp([(q4, MODE_1x1)], qkv3[:, :, C:C + d], out=S, weight_batched=True, a_heads=heads,

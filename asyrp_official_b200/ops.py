@@ -100,6 +100,7 @@ class ConvOp:
         d.weight_ld = weight.stride(-2)
         d.weight_batch_stride = weight.stride(0) if (weight_batched and weight.dim() == 3) else 0
         d.a_heads, d.b_heads, d.out_heads = a_heads, b_heads, out_heads
+        d.out_f32 = int(out is not None and out.dtype == torch.float32)
         d.ebias = ebias.data_ptr() if ebias is not None else None
         d.ebias_stride = ebias_stride
         d.residual = residual.data_ptr() if residual is not None else None

@@ -73,6 +73,7 @@ typedef struct AsyrpConvDesc {
    * b_heads > 1: weights are [N/b_heads][Cout][weight_ld], head h reads columns [h*K, (h+1)*K);
    * out_heads > 1: out is [N/out_heads][H][W][out_heads*Cout], head h writes channels [h*Cout, (h+1)*Cout). */
   int a_heads, b_heads, out_heads;
+  int out_f32;           /* 1: `out` is fp32 NHWC (attention logits); excludes residual / stats / planar */
   const float* ebias;    /* fp32 bias row(s): row n at ebias + n*ebias_stride; NULL = none */
   int ebias_stride;      /* 0: one row shared by all samples (plain bias);
                             >0: per-sample rows (conv bias + timestep-embedding projection) */
@@ -148,7 +149,7 @@ int asyrp_attention(const void* qkv, void* out, int N, int T, int heads, int hea
 
 /* Tensor-core attention glue (single-head blocks with T >= 128: the q k^T and P v GEMMs run on the conv kernel with
  * weight_batched = 1).  asyrp_transpose_tc: [N][T][ld] (first C channels at `in`) -> [N][C][T].
- * asyrp_softmax_rows: P = softmax(scale * S) per row of T <= 1024 fp16 values, fp32 math. */
+ * asyrp_softmax_rows: P (fp16) = softmax(scale * S) per row of T <= 1024 fp32 logits, fp32 math. */
 int asyrp_transpose_tc(const void* in, void* out, int N, int T, int C, int ld, void* stream);
 int asyrp_softmax_rows(const void* S, void* P, long long rows, int T, float scale, void* stream);
 
