@@ -277,6 +277,28 @@ __global__ void ddim_update_kernel(const float* __restrict__ x, const float* __r
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// DDPM ancestral update (utils/diffusion_utils.py:74-82, sampling_type='ddpm'):
+//   mean = 1/sqrt(1-bt) * (x - bt/sqrt(1-at) * et);  x_next = mean + mask * exp(0.5*logvar) * z
+// logvar: the fixed table entry (learn_sigma=False) or, with learn_sigma, channels [Cx, 2Cx) of the model output
+// (the reference uses the raw learned channels as log-variance, :47-51).  mask = 0 at t == 0.
+// ---------------------------------------------------------------------------------------------
+__global__ void ddpm_update_kernel(const float* __restrict__ x, const float* __restrict__ et, const float* __restrict__ z,
+                                   float* __restrict__ x_next, int N, int Cx, int Ce, int HW, float at, float bt,
+                                   float logvar, int learned, float mask) {
+  const float weight = __fdiv_rn(bt, sqrtf(1.0f - at));
+  const float inv = __fdiv_rn(1.0f, sqrtf(1.0f - bt));
+  const size_t total = static_cast<size_t>(N) * Cx * HW;
+  for (size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t n = idx / (static_cast<size_t>(Cx) * HW), r = idx % (static_cast<size_t>(Cx) * HW);
+    const size_t eidx = n * Ce * HW + r;
+    const float mean = __fmul_rn(inv, __fsub_rn(x[idx], __fmul_rn(weight, et[eidx])));
+    const float lv = learned ? et[eidx + static_cast<size_t>(Cx) * HW] : logvar;
+    x_next[idx] = __fadd_rn(mean, __fmul_rn(__fmul_rn(mask, expf(0.5f * lv)), z[idx]));
+  }
+}
+
 // out = alpha*a + beta*b on fp16 tensors (fp32 math): h2 = c0*h + c_i*delta_h_i  (ddpm/diffusion.py:512-516)
 __global__ void axpby_kernel(const __half* __restrict__ a, const __half* __restrict__ b, __half* __restrict__ out,
                              float alpha, float beta, size_t n8) {
@@ -485,6 +507,17 @@ ASYRP_API int asyrp_slerp_h(const void* h, const float* dh, long long dh_sample_
   slerp_h_kernel<<<N, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __half*>(h), dh, dh_sample_stride,
                                                                     static_cast<__half*>(h2), stats, stats_tiles, C, H,
                                                                     W, t, use_mask);
+  ASYRP_CHECK_CUDA(cudaGetLastError());
+  return ASYRP_OK;
+}
+
+ASYRP_API int asyrp_ddpm_update(const float* x, const float* et, const float* z, float* x_next, int N, int Cx, int Ce,
+                                int HW, float at, float bt, float logvar, int learned_sigma, float mask, void* stream) {
+  ASYRP_REQUIRE(z != nullptr, "asyrp_ddpm_update: noise tensor required");
+  ASYRP_REQUIRE(!learned_sigma || Ce >= 2 * Cx, "asyrp_ddpm_update: learned sigma needs 2*Cx model channels");
+  const size_t total = static_cast<size_t>(N) * Cx * HW;
+  ddpm_update_kernel<<<grid_for(total, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, et, z, x_next, N, Cx, Ce, HW, at, bt, logvar, learned_sigma, mask);
   ASYRP_CHECK_CUDA(cudaGetLastError());
   return ASYRP_OK;
 }

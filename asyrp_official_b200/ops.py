@@ -220,3 +220,10 @@ def softmax_rows(S, P, scale):
     lib = _lib.load()
     T = S.shape[-1]
     check(lib.asyrp_softmax_rows(_ptr(S), _ptr(P), S.numel() // T, T, float(scale), _stream()), "asyrp_softmax_rows")
+
+
+def ddpm_update(x, et, z, x_next, at, bt, logvar, learned_sigma, mask):
+    lib = _lib.load()
+    N, Cx, H, W = x.shape
+    check(lib.asyrp_ddpm_update(_ptr(x), _ptr(et), _ptr(z), _ptr(x_next), N, Cx, et.shape[1], H * W, at, bt, logvar,
+                                int(learned_sigma), mask, _stream()), "asyrp_ddpm_update")

@@ -35,8 +35,8 @@ def denoising_step(xt, t, t_next, *, models, logvars=None, b, sampling_type='ddi
     N(0,1) draw the reference takes from torch.randn_like (:97)."""
     if type(image_space_noise) != int:
         raise NotImplementedError("image_space_noise optimisation is a training-side experiment (out of scope)")
-    if sampling_type != 'ddim':
-        raise NotImplementedError("only sampling_type='ddim' is on the Asyrp inference path (script_inference.sh)")
+    if sampling_type not in ('ddim', 'ddpm'):
+        raise ValueError(f"unknown sampling_type {sampling_type!r}")
     model = models.module if hasattr(models, "module") and not hasattr(models, "engine") else models
     et, et_modified, delta_h, middle_h = model(xt, t, index=index, t_edit=t_edit, hs_coeff=hs_coeff, delta_h=delta_h,
                                                ignore_timestep=ignore_timestep, use_mask=use_mask)
@@ -45,6 +45,14 @@ def denoising_step(xt, t, t_next, *, models, logvars=None, b, sampling_type='ddi
     bf = torch.as_tensor(b, dtype=torch.float32).cpu()
     ac = (1.0 - bf).cumprod(dim=0)
     at = ac[ti]
+    if sampling_type == 'ddpm':  # ancestral step (:74-82); x0_t is not produced on this branch
+        xt = xt.to(et.device, torch.float32).contiguous()
+        z = (noise if noise is not None else torch.randn_like(xt)).to(et.device, torch.float32).contiguous()
+        lv = 0.0 if learn_sigma else float(torch.as_tensor(logvars, dtype=torch.float32)[ti])
+        xt_next = torch.empty_like(xt)
+        with torch.cuda.device(et.device):
+            ops.ddpm_update(xt, et, z, xt_next, float(at), float(bf[ti]), lv, learn_sigma, 0.0 if ti == 0 else 1.0)
+        return xt_next, None, delta_h, middle_h
     an = torch.ones_like(at) if tn == -1 else ac[tn]
     if eta == 0:
         c1, c2 = torch.zeros_like(at), (1 - an).sqrt()

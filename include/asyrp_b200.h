@@ -129,6 +129,11 @@ int asyrp_ddim_update(const float* x, const float* et, const float* em, const fl
                       float* x0_out, int N, int Cx, int Ce, int HW, float at, float an, float c1, float c2,
                       void* stream);
 
+/* DDPM ancestral update (utils/diffusion_utils.py:74-82, sampling_type 'ddpm'):
+ *   x_next = (x - bt/sqrt(1-at)*et)/sqrt(1-bt) + mask*exp(0.5*logvar)*z;  learned_sigma: logvar = et channels [Cx, 2Cx) */
+int asyrp_ddpm_update(const float* x, const float* et, const float* z, float* x_next, int N, int Cx, int Ce, int HW,
+                      float at, float bt, float logvar, int learned_sigma, float mask, void* stream);
+
 /* out = alpha*a + beta*b, fp16 tensors of `numel` elements (multiple of 8) */
 int asyrp_axpby(const void* a, const void* b, void* out, float alpha, float beta, long long numel, void* stream);
 
