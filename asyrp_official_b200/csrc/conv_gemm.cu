@@ -75,6 +75,10 @@ struct ConvParams {
   int out_ld;              // elements between consecutive output pixels (Cout * out_heads)
   int out_f32;             // `out` is fp32 (attention logits keep fp32 precision for the softmax)
   int any_transform;       // some segment has an affine: the MMA warp then waits on readyA instead of fullA
+  // K-loop order: entries (segment << 6 | 64-channel chunk).  Short 1x1 stages (one tap of MMA work per TMA load)
+  // are interleaved between the long 3x3 stages so that their loads hide behind the 3x3 MMA phases.
+  int n_sched;
+  uint8_t sched[64];
 };
 
 // SWAP: operand roles exchanged — the weight tile (128 output channels) is the M side and the MT*128 pixels are the
@@ -151,12 +155,13 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
         const int mt = tile % p.m_tiles;
         const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, tn = mt / (p.tiles_x * p.tiles_y);
         const int x0 = tx * p.TW, y0 = ty * THT, n0 = tn * p.NB;
-        for (int s = 0; s < p.nseg; ++s) {
+        for (int e = 0; e < p.n_sched; ++e) {
+          const int s = p.sched[e] >> 6, ch = p.sched[e] & 63;
           const ConvSegDev sg = p.seg[s];
           const int ncopies = (sg.mode == 0 || sg.mode == 3) ? 1 : (sg.mode == 1 ? 3 : 9);
           const uint32_t a_bytes = sg.mode == 3 ? (THT + 2) * (p.TW + 2) * 128u
                                                 : (sg.mode == 1 ? (THT + 2) : THT) * p.row_bytes;
-          for (int ch = 0; ch < sg.nchunks; ++ch) {
+          {
             for (int cp = 0; cp < ncopies; ++cp) {
               mbar_wait(&emptyA[sa], pa ^ 1);
               mbar_arrive_expect_tx(&fullA[sa], a_bytes);
@@ -188,11 +193,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
         const int tn = mt / (p.tiles_x * p.tiles_y);
         const int bz = p.b_batched ? tn * p.NB : 0;
         const int b_n = bz / p.b_heads, b_h = bz % p.b_heads;
-        for (int s = 0; s < p.nseg; ++s) {
+        for (int e = 0; e < p.n_sched; ++e) {
+          const int s = p.sched[e] >> 6, ch = p.sched[e] & 63;
           const ConvSegDev sg = p.seg[s];
           const int ncopies = (sg.mode == 0 || sg.mode == 3) ? 1 : (sg.mode == 1 ? 3 : 9);
           const int ntaps = sg.mode == 1 ? 3 : (sg.mode == 3 ? 9 : 1);
-          for (int ch = 0; ch < sg.nchunks; ++ch) {
+          {
             for (int cp = 0; cp < ncopies; ++cp) {
               for (int tp = 0; tp < ntaps; ++tp) {
                 // tap index in the weight matrix: ky*3+kx
@@ -221,7 +227,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * kAccCols;
         uint32_t accumulate = 0;
-        for (int s = 0; s < p.nseg; ++s) {
+        for (int e = 0; e < p.n_sched; ++e) {
+          const int s = p.sched[e] >> 6, ch = p.sched[e] & 63;
           const ConvSegDev sg = p.seg[s];
           const int ncopies = (sg.mode == 0 || sg.mode == 3) ? 1 : (sg.mode == 1 ? 3 : 9);
           const int ntaps = sg.mode == 1 ? 3 : (sg.mode == 3 ? 9 : 1);
@@ -229,7 +236,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
           const uint32_t halo_pitch = (p.TW + 2) * 128u;
           const uint32_t sbo = sg.mode == 3 ? halo_pitch : 1024u;
           const uint32_t sub_stride = sg.mode == 3 ? p.TH * halo_pitch : p.TH * p.row_bytes;
-          for (int ch = 0; ch < sg.nchunks; ++ch) {
+          {
             for (int cp = 0; cp < ncopies; ++cp) {
               mbar_wait(p.any_transform ? &readyA[sa] : &fullA[sa], pa);
               tc_fence_after();
@@ -282,7 +289,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
         const int mt = tile % p.m_tiles;
         const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, tn = mt / (p.tiles_x * p.tiles_y);
         const int x0 = tx * p.TW, y0 = ty * THT, n0 = tn * p.NB;
-        for (int s = 0; s < p.nseg; ++s) {
+        for (int e = 0; e < p.n_sched; ++e) {
+          const int s = p.sched[e] >> 6, ch = p.sched[e] & 63;
           const ConvSegDev sg = p.seg[s];
           const int ncopies = (sg.mode == 0 || sg.mode == 3) ? 1 : (sg.mode == 1 ? 3 : 9);
           const int pw = sg.mode == 3 ? p.TW + 2 : p.TW;      // pixels per (row, sample) in the stage
@@ -290,7 +298,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
           const int rows = (sg.mode == 1 || sg.mode == 3) ? THT + 2 : THT;
           const int npix = rows * prow;
           const int yoff = (sg.mode == 1 || sg.mode == 3) ? -1 : 0;
-          for (int ch = 0; ch < sg.nchunks; ++ch) {
+          {
             float ca[8], cb[8];
             if (sg.affine != nullptr && p.NB == 1) {
               const float4* ap = reinterpret_cast<const float4*>(
@@ -830,6 +838,24 @@ ASYRP_API int asyrp_conv_create(const AsyrpConvDesc* d, void** out_op) {
     int rc = encode_tensor_map(&p.tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, d->weight, dims, strides, box,
                                CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != ASYRP_OK) { delete op; return rc; }
+  }
+  {
+    // K-loop schedule: heavy chunks (3x3 taps) in order, light chunks (1x1 segments) spread evenly between them
+    uint8_t heavy[64], light[64];
+    int nh = 0, nl = 0;
+    for (int sg_ = 0; sg_ < d->nseg; ++sg_)
+      for (int ch = 0; ch < p.seg[sg_].nchunks; ++ch) {
+        ASYRP_REQUIRE(nh + nl < 64 && ch < 64, "asyrp_conv_create: more than 64 K chunks (%d channels) per tile", ktot);
+        (p.seg[sg_].mode == 0 ? light[nl++] : heavy[nh++]) = static_cast<uint8_t>((sg_ << 6) | ch);
+      }
+    int il = 0, n = 0;
+    for (int ih = 0; ih < nh; ++ih) {
+      p.sched[n++] = heavy[ih];
+      const int upto = (nl * (ih + 1)) / nh;  // light chunks due after this heavy chunk
+      while (il < upto) p.sched[n++] = light[il++];
+    }
+    while (il < nl) p.sched[n++] = light[il++];
+    p.n_sched = n;
   }
   p.b_batched = d->weight_batched;
   p.a_heads = d->a_heads > 1 ? d->a_heads : 1;
