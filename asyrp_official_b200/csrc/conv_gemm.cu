@@ -75,8 +75,8 @@ struct ConvParams {
   int out_ld;              // elements between consecutive output pixels (Cout * out_heads)
   int out_f32;             // `out` is fp32 (attention logits keep fp32 precision for the softmax)
   int any_transform;       // some segment has an affine: the MMA warp then waits on readyA instead of fullA
-  // K-loop order: entries (segment << 6 | 64-channel chunk).  Short 1x1 stages (one tap of MMA work per TMA load)
-  // are interleaved between the long 3x3 stages so that their loads hide behind the 3x3 MMA phases.
+  // K-loop order: entries (segment << 6 | 64-channel chunk).  Measured on B200 (round 1): interleaving the short 1x1
+  // stages between the long 3x3 stages was neutral-to-negative, so the order is 3x3 chunks first, 1x1 chunks last.
   int n_sched;
   uint8_t sched[64];
 };
@@ -840,7 +840,7 @@ ASYRP_API int asyrp_conv_create(const AsyrpConvDesc* d, void** out_op) {
     if (rc != ASYRP_OK) { delete op; return rc; }
   }
   {
-    // K-loop schedule: heavy chunks (3x3 taps) in order, light chunks (1x1 segments) spread evenly between them
+    // K-loop schedule: heavy chunks (3x3 taps) in order, then the light chunks (1x1 segments)
     uint8_t heavy[64], light[64];
     int nh = 0, nl = 0;
     for (int sg_ = 0; sg_ < d->nseg; ++sg_)
@@ -851,7 +851,7 @@ ASYRP_API int asyrp_conv_create(const AsyrpConvDesc* d, void** out_op) {
     int il = 0, n = 0;
     for (int ih = 0; ih < nh; ++ih) {
       p.sched[n++] = heavy[ih];
-      const int upto = (nl * (ih + 1)) / nh;  // light chunks due after this heavy chunk
+      const int upto = (ih == nh - 1) ? nl : 0;  // light chunks after the last heavy chunk
       while (il < upto) p.sched[n++] = light[il++];
     }
     while (il < nl) p.sched[n++] = light[il++];
