@@ -81,6 +81,64 @@ struct ConvParams {
   uint8_t sched[64];
 };
 
+// Swapped-operand epilogue of one warp: TMEM lane = output channel c, columns = the tile's pixels (row-major in the
+// TW x (MT*128/TW) tile); this warp drains the 32-pixel column chunks half, half+2, ...  TWS = log2(TW).
+template <int TWS, int MT>
+__device__ __forceinline__ void swap_epilogue(const ConvParams& p, uint32_t taddr, int half, int tn, int y0, int x0,
+                                              int c, int lane_off, uint32_t sel, float eb, float& s1, float& s2) {
+  constexpr int TW = 1 << TWS;
+  constexpr int kRows = 32 / TW;  // image rows per 32-pixel chunk
+  const int cout = p.Cout;
+  const int row_stride = p.W * cout;
+  const float scale = p.acc_scale, rs = p.res_scale;
+  const __half* __restrict__ resp = p.res;
+  __half* __restrict__ outp = p.out;
+#pragma unroll 1
+  for (int cc = half; cc < (MT * 128) / 32; cc += 2) {
+    uint32_t r[32];
+    tmem_ld_32x32(taddr + cc * 32, r);
+    // element offset of the chunk's first pixel, channel c
+    const size_t o0 = ((static_cast<size_t>(tn) * p.H + y0 + cc * kRows) * p.W + x0) * cout + c;
+    __half2 rv[16];
+    if (resp != nullptr) {  // all residual loads first: independent of the stores below
+      const __half* rp = resp + o0;
+#pragma unroll
+      for (int i = 0; i < 32; i += 2)
+        rv[i >> 1] = __halves2half2(rp[(i >> TWS) * row_stride + (i & (TW - 1)) * cout],
+                                    rp[((i + 1) >> TWS) * row_stride + ((i + 1) & (TW - 1)) * cout]);
+    }
+    tmem_ld_wait();
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = fmaf(__uint_as_float(r[i]), scale, eb);
+    if (resp != nullptr) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) {
+        const float2 f = __half22float2(rv[i >> 1]);
+        v[i] = fmaf(rs, f.x, v[i]);
+        v[i + 1] = fmaf(rs, f.y, v[i + 1]);
+      }
+    }
+    __half* lp = outp + o0 + lane_off;
+#pragma unroll
+    for (int dy = 0; dy < kRows; ++dy) {
+      __half* rowp = lp + dy * row_stride;
+#pragma unroll
+      for (int dx = 0; dx < TW; dx += 2) {
+        const int i = dy * TW + dx;
+        const __half2 mine = __floats2half2_rn(v[i], v[i + 1]);  // (pixel i, pixel i+1) of this lane's channel
+        const uint32_t x = *reinterpret_cast<const uint32_t*>(&mine);
+        const uint32_t y = __shfl_xor_sync(0xffffffffu, x, 1);
+        // even lane: (own, partner) at pixel i; odd lane: (partner, own) at pixel i+1
+        *reinterpret_cast<uint32_t*>(rowp + dx * cout) = __byte_perm(x, y, sel);
+        s1 += v[i] + v[i + 1];
+        s2 = fmaf(v[i], v[i], s2);
+        s2 = fmaf(v[i + 1], v[i + 1], s2);
+      }
+    }
+  }
+}
+
 // SWAP: operand roles exchanged — the weight tile (128 output channels) is the M side and the MT*128 pixels are the
 // N side of ONE N=256 MMA per K step, so D is [channel lane][pixel column].  Per MMA the tensor core then reads
 // 4 KB (weights) + 8 KB (pixels) of shared memory per 128 cycles instead of 4 + 4 KB per 64 cycles: the Cout=128
@@ -163,7 +221,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
                                                 : (sg.mode == 1 ? (THT + 2) : THT) * p.row_bytes;
           {
             for (int cp = 0; cp < ncopies; ++cp) {
-              mbar_wait(&emptyA[sa], pa ^ 1);
+              mbar_wait_suspend(&emptyA[sa], pa ^ 1);
               mbar_arrive_expect_tx(&fullA[sa], a_bytes);
               uint8_t* dst = sA + sa * p.a_stage_bytes;
               if (sg.mode == 3) {
@@ -203,7 +261,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
               for (int tp = 0; tp < ntaps; ++tp) {
                 // tap index in the weight matrix: ky*3+kx
                 const int tap = sg.mode == 0 ? 0 : (sg.mode == 1 ? tp * 3 + cp : (sg.mode == 3 ? tp : cp));
-                mbar_wait(&emptyB[sb], pb ^ 1);
+                mbar_wait_suspend(&emptyB[sb], pb ^ 1);
                 mbar_arrive_expect_tx(&fullB[sb], kBStage);
                 tma_load_4d(sB + sb * kBStage, &p.tmB, &fullB[sb], sg.kbase + tap * sg.C + ch * 64, nt * BN, b_h, b_n);
                 if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
@@ -217,13 +275,14 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
     // ======================================================== MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_f16_m128(SWAP ? MT * 128 : BN);
+      const uint32_t b_lo0 = umma_desc_lo(smem_u32(sB));
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       int it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
-        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        mbar_wait_suspend(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * kAccCols;
         uint32_t accumulate = 0;
@@ -236,36 +295,41 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
           const uint32_t halo_pitch = (p.TW + 2) * 128u;
           const uint32_t sbo = sg.mode == 3 ? halo_pitch : 1024u;
           const uint32_t sub_stride = sg.mode == 3 ? p.TH * halo_pitch : p.TH * p.row_bytes;
+          // descriptors as (lo, hi) words: only the start-address field (16-byte units) changes inside the loop
+          const uint32_t a_hi = umma_desc_hi(sbo), b_hi = umma_desc_hi(1024u);
+          const uint32_t sub16 = sub_stride >> 4;
+          // tap step in 16-byte units.  mode 1: dy tap = row shift inside the dx copy; mode 3: (ky, kx) = pixel
+          // offset inside the halo tile: +128 B per kx, and from kx=2 to the next ky row +halo_pitch-256 B
+          const uint32_t step16 = sg.mode == 3 ? 8u : (p.row_bytes >> 4);
+          const uint32_t wrap16 = sg.mode == 3 ? ((halo_pitch - 256u) >> 4) : step16;
           {
             for (int cp = 0; cp < ncopies; ++cp) {
               mbar_wait(p.any_transform ? &readyA[sa] : &fullA[sa], pa);
               tc_fence_after();
-              const uint32_t a_base = smem_u32(sA + sa * p.a_stage_bytes);
+              uint32_t a_lo = umma_desc_lo(smem_u32(sA + sa * p.a_stage_bytes));
+              int kx = 0;
               for (int tp = 0; tp < ntaps; ++tp) {
                 mbar_wait(&fullB[sb], pb);
                 tc_fence_after();
-                const uint32_t b_addr = smem_u32(sB + sb * kBStage);
-                // mode 1: dy tap = row shift inside the dx copy; mode 3: (ky, kx) = pixel offset inside the halo tile
-                const uint32_t tap_off = sg.mode == 3 ? (tp / 3) * halo_pitch + (tp % 3) * 128u : tp * p.row_bytes;
+                const uint32_t b_lo = b_lo0 + sb * (kBStage >> 4);
                 if constexpr (SWAP) {
                   // M = 128 weight rows, N = all MT*128 pixel rows (uniform 8-row-group pitch across sub-tiles)
 #pragma unroll
                   for (int k = 0; k < 4; ++k)
-                    umma_f16(d_tmem, umma_desc_k128(b_addr + k * 32), umma_desc_k128(a_base + tap_off + k * 32, sbo),
-                             idesc, (accumulate | k) ? 1u : 0u);
+                    umma_f16_w(d_tmem, b_lo + 2 * k, b_hi, a_lo + 2 * k, a_hi, idesc, (accumulate | k) ? 1u : 0u);
                 } else {
 #pragma unroll
                   for (int sub = 0; sub < MT; ++sub) {
-                    const uint32_t a_addr = a_base + sub * sub_stride + tap_off;
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                      umma_f16(d_tmem + sub * BN, umma_desc_k128(a_addr + k * 32, sbo),
-                               umma_desc_k128(b_addr + k * 32), idesc, (accumulate | k) ? 1u : 0u);
+                      umma_f16_w(d_tmem + sub * BN, a_lo + sub * sub16 + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc,
+                                 (accumulate | k) ? 1u : 0u);
                   }
                 }
                 accumulate = 1;
                 umma_commit(&emptyB[sb]);
                 if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
+                if (++kx == 3) { kx = 0; a_lo += wrap16; } else { a_lo += step16; }
               }
               umma_commit(&emptyA[sa]);
               if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
@@ -310,7 +374,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
               }
             }
             for (int cp = 0; cp < ncopies; ++cp) {
-              mbar_wait(&fullA[sa], pa);
+              mbar_wait_suspend(&fullA[sa], pa);
               if (sg.affine != nullptr) {
                 uint8_t* stage = sA + sa * p.a_stage_bytes;
                 const int xoff = sg.mode == 3 ? -1 : (sg.mode == 1 ? cp - 1 : 0);
@@ -412,59 +476,27 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
       const int tile_in_sample = ty * p.tiles_x + tx;
       float* st = s_stats + acc * (4 * BN);
 
-      mbar_wait(&tfull[acc], acc_phase);
+      mbar_wait_suspend(&tfull[acc], acc_phase);
       tc_fence_after();
       if constexpr (SWAP) {
-        // thread = output channel (TMEM lane), registers = 32 consecutive pixels of the 8(16)-wide x 32-tall tile
+        // thread = output channel (TMEM lane), registers = 32 consecutive pixels of the 8(16)-wide x 32(16)-tall
+        // tile.  The swapped tile is only selected when it lies fully inside the image (conv_config), so there are
+        // no bounds predicates here: this epilogue is instruction-issue bound (it set a ~9 us floor per tile).
         const int c = nt * 128 + q * 32 + lane;
-        const float eb = p.ebias != nullptr ? p.ebias[static_cast<size_t>(tn) * p.ebias_stride + c] : 0.f;
-        float s1 = 0.f, s2 = 0.f;
-        const int tws = 31 - __clz(p.TW);  // TW is 8 or 16
-        const size_t row_stride = static_cast<size_t>(p.W) * p.Cout;
-        const __half* __restrict__ resp = p.res;
-        __half* __restrict__ outp = p.out;
+        const float eb = (p.ebias != nullptr ? p.ebias[static_cast<size_t>(tn) * p.ebias_stride + c] : 0.f) *
+                         p.acc_scale;
         const bool odd = (lane & 1) != 0;
-#pragma unroll 1
-        for (int cc = half; cc < (MT * 128) / 32; cc += 2) {
-          uint32_t r[32];
-          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kAccCols + cc * 32, r);
-          // element offset of the chunk's first pixel (32 pixels = 32/TW image rows of the tile)
-          const int py0 = ty * THT + ((cc * 32) >> tws), px0 = tx * p.TW;
-          const size_t o0 = ((static_cast<size_t>(tn) * p.H + py0) * p.W + px0) * p.Cout + c;
-          float rv[32];
-          if (resp != nullptr) {  // all residual loads first: independent of the stores below
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const int dy = i >> tws, dx = i & (p.TW - 1);
-              rv[i] = (px0 + dx < p.W && py0 + dy < p.H) ? __half2float(resp[o0 + dy * row_stride + dx * p.Cout]) : 0.f;
-            }
-          }
-          tmem_ld_wait();
-          float v[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            v[i] = (__uint_as_float(r[i]) + eb) * p.acc_scale;
-            if (resp != nullptr) v[i] += p.res_scale * rv[i];
-          }
-          // lanes (2j, 2j+1) hold adjacent channels: exchange so that the even lane stores pixel i and the odd lane
-          // pixel i+1, each as one half2 (4 B) -> a warp store covers two pixels x 64 B
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const float mine = odd ? v[i + 1] : v[i];
-            const float give = odd ? v[i] : v[i + 1];
-            const float got = __shfl_xor_sync(0xffffffffu, give, 1);
-            const int ii = odd ? i + 1 : i;
-            const int dy = ii >> tws, dx = ii & (p.TW - 1);
-            const bool ok0 = (px0 + (i & (p.TW - 1)) < p.W) && (py0 + (i >> tws) < p.H);
-            const bool ok1 = (px0 + ((i + 1) & (p.TW - 1)) < p.W) && (py0 + ((i + 1) >> tws) < p.H);
-            if (odd ? ok1 : ok0) {
-              const __half2 h2 = odd ? __floats2half2_rn(got, mine) : __floats2half2_rn(mine, got);
-              *reinterpret_cast<__half2*>(outp + (o0 - (odd ? 1 : 0)) + dy * row_stride + dx * p.Cout) = h2;
-            }
-            if (ok0) { s1 += v[i]; s2 += v[i] * v[i]; }
-            if (ok1) { s1 += v[i + 1]; s2 += v[i + 1] * v[i + 1]; }
-          }
-        }
+        // lanes (2j, 2j+1) hold adjacent channels: the even lane stores pixel i, the odd lane pixel i+1, each as one
+        // half2 (channel pair) -> a warp store covers two pixels x 64 B
+        const uint32_t sel = odd ? 0x3276u : 0x5410u;
+        const int lane_off = odd ? p.Cout - 1 : 0;
+        float s1 = 0.f, s2 = 0.f;
+        if (p.TW == 8)
+          swap_epilogue<3, MT>(p, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kAccCols, half, tn,
+                               ty * THT, tx * 8, c, lane_off, sel, eb, s1, s2);
+        else
+          swap_epilogue<4, MT>(p, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kAccCols, half, tn,
+                               ty * THT, tx * 16, c, lane_off, sel, eb, s1, s2);
         if (p.stats != nullptr) {
           // channel pair = lanes (2j, 2j+1); each (tile, half) owns one slot: nothing to reduce across warps
           s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
@@ -710,7 +742,8 @@ static void conv_config(int H, int W, int Cout, int halo, int* BN, int* MT) {
   for (int i = 0; i < 5; ++i) {
     const int bn = cand[i][0], mt = cand[i][1];
     if (Cout % bn != 0) continue;
-    if (mt == 2 && !(NB == 1 && H > 1 && H % (2 * TH) == 0)) continue;
+    // two stacked sub-tiles: whole tiles only (the swapped-operand epilogue has no bounds predicates)
+    if (mt == 2 && !(NB == 1 && H > 1 && H % (2 * TH) == 0 && W % TW == 0)) continue;
     const int tiles = tiles_x * ((H + TH * mt - 1) / (TH * mt)) * tiles_n * (Cout / bn);
     if (tiles >= 120) { best = i; break; }
     if (tiles > best_tiles) { best = i; best_tiles = tiles; }

@@ -42,6 +42,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// try_wait with a suspend-time hint (ns): the waiting thread may stay suspended until the phase completes instead
+// of re-issuing the poll every ~14 cycles (three issue slots each, taken from the epilogue warps of the same SMSP).
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_suspend(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait_hint(bar, parity, 20000u)) {
+  }
+}
 
 // ---------------------------------------------------------------- proxy fences
 // generic-proxy smem writes -> visible to the async proxy (TMA / tcgen05 operand reads)
@@ -106,6 +123,18 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// same, descriptors given as (lo, hi) words: the K-loop only ever changes the 14-bit start-address field (lo)
+__device__ __forceinline__ void umma_f16_w(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                           uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // arrive on an mbarrier when all previously issued tcgen05 async ops of this thread complete
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
@@ -143,6 +172,13 @@ __device__ __forceinline__ uint64_t umma_desc_k128(uint32_t smem_addr, uint32_t 
   d |= static_cast<uint64_t>(1) << 46;            // descriptor version (Blackwell)
   d |= static_cast<uint64_t>(2) << 61;            // SWIZZLE_128B
   return d;
+}
+// the two 32-bit words of umma_desc_k128(): lo = start address field (+ LBO), hi = SBO / version / swizzle mode
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr) {
+  return ((smem_addr & 0x3FFFF) >> 4) | (1u << 16);
+}
+__device__ __forceinline__ uint32_t umma_desc_hi(uint32_t sbo_bytes) {
+  return (sbo_bytes >> 4) | (1u << 14) | (2u << 29);
 }
 // Instruction descriptor for kind::f16: fp16 A/B (K-major), fp32 D, M=128, N=n.
 __host__ __device__ constexpr uint32_t umma_idesc_f16_m128(uint32_t n) {
