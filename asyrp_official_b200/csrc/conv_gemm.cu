@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
   // SWIZZLE_128B operands need 1024B alignment
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = uniform_warp_id();
   const int lane = threadIdx.x & 31;
   constexpr uint32_t kBStage = BN * 128;
   static_assert(!SWAP || (BN == 128 && MT == 2), "swapped-operand variant: 128 channels x 256 pixels");
@@ -206,7 +206,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
     // ======================================================== TMA producer, A operand (activations)
     // A and B have independent rings and independent producer threads, so the activation prefetch (which the
     // transform warps must also touch) runs a full A-ring ahead regardless of the weight ring's depth.
-    if (lane == 0) {
+    // Whole warp, uniform control flow; one elected lane issues (see elect_one()).
+    {
       int sa = 0;
       uint32_t pa = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -222,18 +223,21 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
           {
             for (int cp = 0; cp < ncopies; ++cp) {
               mbar_wait_suspend(&emptyA[sa], pa ^ 1);
-              mbar_arrive_expect_tx(&fullA[sa], a_bytes);
               uint8_t* dst = sA + sa * p.a_stage_bytes;
+              int c0 = ch * 64, c1, c2 = n0, c3 = 0, c4;
               if (sg.mode == 3) {
-                tma_load_5d(dst, &p.tmA[s], &fullA[sa], ch * 64, x0 - 1, n0, 0, y0 - 1);
+                c1 = x0 - 1; c4 = y0 - 1;
               } else if (sg.mode == 0) {
-                tma_load_5d(dst, &p.tmA[s], &fullA[sa], ch * 64, x0, n0 / p.a_heads, n0 % p.a_heads, y0);
+                c1 = x0; c2 = n0 / p.a_heads; c3 = n0 % p.a_heads; c4 = y0;
               } else if (sg.mode == 1) {
-                tma_load_5d(dst, &p.tmA[s], &fullA[sa], ch * 64, x0 + cp - 1, n0, 0, y0 - 1);
+                c1 = x0 + cp - 1; c4 = y0 - 1;
               } else {
                 const int ky = cp / 3, kx = cp % 3;
-                tma_load_5d(dst, &p.tmA[s], &fullA[sa], ch * 64 + (kx & 1) * sg.C, x0 + (kx >> 1), n0, ky & 1,
-                            y0 + (ky >> 1));
+                c0 += (kx & 1) * sg.C; c1 = x0 + (kx >> 1); c3 = ky & 1; c4 = y0 + (ky >> 1);
+              }
+              if (elect_one()) {
+                mbar_arrive_expect_tx(&fullA[sa], a_bytes);
+                tma_load_5d(dst, &p.tmA[s], &fullA[sa], c0, c1, c2, c3, c4);
               }
               if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
             }
@@ -243,7 +247,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
     }
   } else if (warp == kWarpB) {
     // ======================================================== TMA producer, B operand (weights)
-    if (lane == 0) {
+    {
       int sb = 0;
       uint32_t pb = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -262,8 +266,11 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
                 // tap index in the weight matrix: ky*3+kx
                 const int tap = sg.mode == 0 ? 0 : (sg.mode == 1 ? tp * 3 + cp : (sg.mode == 3 ? tp : cp));
                 mbar_wait_suspend(&emptyB[sb], pb ^ 1);
-                mbar_arrive_expect_tx(&fullB[sb], kBStage);
-                tma_load_4d(sB + sb * kBStage, &p.tmB, &fullB[sb], sg.kbase + tap * sg.C + ch * 64, nt * BN, b_h, b_n);
+                if (elect_one()) {
+                  mbar_arrive_expect_tx(&fullB[sb], kBStage);
+                  tma_load_4d(sB + sb * kBStage, &p.tmB, &fullB[sb], sg.kbase + tap * sg.C + ch * 64, nt * BN, b_h,
+                              b_n);
+                }
                 if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
               }
             }
@@ -272,8 +279,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
       }
     }
   } else if (warp == 1) {
-    // ======================================================== MMA issuer
-    if (lane == 0) {
+    // ======================================================== MMA issuer (whole warp, elected lane issues)
+    {
       constexpr uint32_t idesc = umma_idesc_f16_m128(SWAP ? MT * 128 : BN);
       const uint32_t b_lo0 = umma_desc_lo(smem_u32(sB));
       int sa = 0, sb = 0;
@@ -312,31 +319,33 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
                 mbar_wait(&fullB[sb], pb);
                 tc_fence_after();
                 const uint32_t b_lo = b_lo0 + sb * (kBStage >> 4);
-                if constexpr (SWAP) {
-                  // M = 128 weight rows, N = all MT*128 pixel rows (uniform 8-row-group pitch across sub-tiles)
-#pragma unroll
-                  for (int k = 0; k < 4; ++k)
-                    umma_f16_w(d_tmem, b_lo + 2 * k, b_hi, a_lo + 2 * k, a_hi, idesc, (accumulate | k) ? 1u : 0u);
-                } else {
-#pragma unroll
-                  for (int sub = 0; sub < MT; ++sub) {
+                if (elect_one()) {
+                  if constexpr (SWAP) {
+                    // M = 128 weight rows, N = all MT*128 pixel rows (uniform 8-row-group pitch across sub-tiles)
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                      umma_f16_w(d_tmem + sub * BN, a_lo + sub * sub16 + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc,
-                                 (accumulate | k) ? 1u : 0u);
+                      umma_f16_w(d_tmem, b_lo + 2 * k, b_hi, a_lo + 2 * k, a_hi, idesc, (accumulate | k) ? 1u : 0u);
+                  } else {
+#pragma unroll
+                    for (int sub = 0; sub < MT; ++sub) {
+#pragma unroll
+                      for (int k = 0; k < 4; ++k)
+                        umma_f16_w(d_tmem + sub * BN, a_lo + sub * sub16 + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc,
+                                   (accumulate | k) ? 1u : 0u);
+                    }
                   }
+                  umma_commit(&emptyB[sb]);
                 }
                 accumulate = 1;
-                umma_commit(&emptyB[sb]);
                 if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
                 if (++kx == 3) { kx = 0; a_lo += wrap16; } else { a_lo += step16; }
               }
-              umma_commit(&emptyA[sa]);
+              if (elect_one()) umma_commit(&emptyA[sa]);
               if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
             }
           }
         }
-        umma_commit(&tfull[acc]);
+        if (elect_one()) umma_commit(&tfull[acc]);
       }
     }
     __syncwarp();

@@ -13,6 +13,24 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 
+// Warp index as a value the compiler can prove warp-uniform (so role branches are uniform branches and everything
+// computed inside them from uniform inputs lives in uniform registers).
+__device__ __forceinline__ int uniform_warp_id() { return __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0); }
+
+// elect.sync: true in exactly one lane of a converged warp.  The single-thread instructions (tcgen05.mma / commit,
+// TMA) take uniform-register operands: issued from warp-uniform control flow under this predicate they compile to
+// a plain predicated instruction; issued from an `if (lane == 0)` branch the compiler wraps every one of them in
+// a vote / R2UR / BRA.U.ANY "waterfall" loop (~140 cycles per MMA: the K loop of the N<=128 tiles was bound by it).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, px;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
