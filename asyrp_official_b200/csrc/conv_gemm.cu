@@ -58,6 +58,12 @@ struct ConvParams {
   int tiles_x, tiles_y, tiles_n, m_tiles, n_tiles;
   int a_stages, b_stages;
   uint32_t a_stage_bytes;  // ring slot size for A copies
+  // Optional second activation ring for the 1x1 ("light") stages of a halo-tile conv.  A light stage is consumed in
+  // 4 MMAs; a heavy (3x3 halo) stage needs load + in-place transform + 36 MMAs.  In one shared ring the light stages
+  // of tile i occupy the slots the first heavy stage of tile i+1 should already be loading / transforming into, and
+  // the tensor pipe idles for that latency at every tile boundary.  l_stages == 0: single ring.
+  int l_stages;
+  uint32_t l_stage_bytes;
   uint32_t row_bytes;      // NB*TW*128 : bytes of one tile row (all samples) of one 64-channel chunk
   const float* ebias;      // fp32 bias (+ timestep-embedding projection): row n at ebias + n*ebias_stride
   int ebias_stride;        // 0: one row shared by all samples
@@ -75,8 +81,7 @@ struct ConvParams {
   int out_ld;              // elements between consecutive output pixels (Cout * out_heads)
   int out_f32;             // `out` is fp32 (attention logits keep fp32 precision for the softmax)
   int any_transform;       // some segment has an affine: the MMA warp then waits on readyA instead of fullA
-  // K-loop order: entries (segment << 6 | 64-channel chunk).  Measured on B200 (round 1): interleaving the short 1x1
-  // stages between the long 3x3 stages was neutral-to-negative, so the order is 3x3 chunks first, 1x1 chunks last.
+  // K-loop order: entries (segment << 6 | 64-channel chunk), see asyrp_conv_create().
   int n_sched;
   uint8_t sched[64];
 };
@@ -158,12 +163,14 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
   static_assert(kTmemCols <= 512 && kTmemCols >= 32, "TMEM budget");
 
   uint8_t* sA = smem;
-  uint8_t* sB = sA + p.a_stages * p.a_stage_bytes;
+  uint8_t* sL = sA + p.a_stages * p.a_stage_bytes;  // light ring (may be empty)
+  uint8_t* sB = sL + p.l_stages * p.l_stage_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sB + p.b_stages * kBStage);
+  const int n_aslots = p.a_stages + p.l_stages;     // barrier index: heavy slots first, then light slots
   uint64_t* fullA = bars;
-  uint64_t* emptyA = fullA + p.a_stages;
-  uint64_t* readyA = emptyA + p.a_stages;
-  uint64_t* fullB = readyA + p.a_stages;
+  uint64_t* emptyA = fullA + n_aslots;
+  uint64_t* readyA = emptyA + n_aslots;
+  uint64_t* fullB = readyA + n_aslots;
   uint64_t* emptyB = fullB + p.b_stages;
   uint64_t* tfull = emptyB + p.b_stages;
   uint64_t* tempty = tfull + 2;
@@ -172,7 +179,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
   const int THT = MT * p.TH;  // rows of the CTA tile
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < p.a_stages; ++i) {
+    for (int i = 0; i < n_aslots; ++i) {
       mbar_init(&fullA[i], 1);
       mbar_init(&emptyA[i], 1);
       mbar_init(&readyA[i], kNumTransformWarps);
@@ -208,8 +215,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
     // transform warps must also touch) runs a full A-ring ahead regardless of the weight ring's depth.
     // Whole warp, uniform control flow; one elected lane issues (see elect_one()).
     {
-      int sa = 0;
-      uint32_t pa = 0;
+      int sa = 0, sl = 0;      // heavy / light ring cursors
+      uint32_t pa = 0, pl = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int mt = tile % p.m_tiles;
         const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, tn = mt / (p.tiles_x * p.tiles_y);
@@ -217,13 +224,15 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
         for (int e = 0; e < p.n_sched; ++e) {
           const int s = p.sched[e] >> 6, ch = p.sched[e] & 63;
           const ConvSegDev sg = p.seg[s];
+          const bool lt = p.l_stages != 0 && sg.mode == 0;
           const int ncopies = (sg.mode == 0 || sg.mode == 3) ? 1 : (sg.mode == 1 ? 3 : 9);
           const uint32_t a_bytes = sg.mode == 3 ? (THT + 2) * (p.TW + 2) * 128u
                                                 : (sg.mode == 1 ? (THT + 2) : THT) * p.row_bytes;
           {
             for (int cp = 0; cp < ncopies; ++cp) {
-              mbar_wait_suspend(&emptyA[sa], pa ^ 1);
-              uint8_t* dst = sA + sa * p.a_stage_bytes;
+              const int slot = lt ? p.a_stages + sl : sa;
+              mbar_wait_suspend(&emptyA[slot], (lt ? pl : pa) ^ 1);
+              uint8_t* dst = lt ? sL + sl * p.l_stage_bytes : sA + sa * p.a_stage_bytes;
               int c0 = ch * 64, c1, c2 = n0, c3 = 0, c4;
               if (sg.mode == 3) {
                 c1 = x0 - 1; c4 = y0 - 1;
@@ -236,10 +245,14 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
                 c0 += (kx & 1) * sg.C; c1 = x0 + (kx >> 1); c3 = ky & 1; c4 = y0 + (ky >> 1);
               }
               if (elect_one()) {
-                mbar_arrive_expect_tx(&fullA[sa], a_bytes);
-                tma_load_5d(dst, &p.tmA[s], &fullA[sa], c0, c1, c2, c3, c4);
+                mbar_arrive_expect_tx(&fullA[slot], a_bytes);
+                tma_load_5d(dst, &p.tmA[s], &fullA[slot], c0, c1, c2, c3, c4);
               }
-              if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
+              if (lt) {
+                if (++sl == p.l_stages) { sl = 0; pl ^= 1; }
+              } else {
+                if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
+              }
             }
           }
         }
@@ -283,8 +296,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
     {
       constexpr uint32_t idesc = umma_idesc_f16_m128(SWAP ? MT * 128 : BN);
       const uint32_t b_lo0 = umma_desc_lo(smem_u32(sB));
-      int sa = 0, sb = 0;
-      uint32_t pa = 0, pb = 0;
+      int sa = 0, sl = 0, sb = 0;
+      uint32_t pa = 0, pl = 0, pb = 0;
       int it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         const int acc = it & 1;
@@ -296,6 +309,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
         for (int e = 0; e < p.n_sched; ++e) {
           const int s = p.sched[e] >> 6, ch = p.sched[e] & 63;
           const ConvSegDev sg = p.seg[s];
+          const bool lt = p.l_stages != 0 && sg.mode == 0;
           const int ncopies = (sg.mode == 0 || sg.mode == 3) ? 1 : (sg.mode == 1 ? 3 : 9);
           const int ntaps = sg.mode == 1 ? 3 : (sg.mode == 3 ? 9 : 1);
           // byte strides inside the A stage: between 8-row groups, between sub-tiles, per ky / kx tap step
@@ -311,9 +325,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
           const uint32_t wrap16 = sg.mode == 3 ? ((halo_pitch - 256u) >> 4) : step16;
           {
             for (int cp = 0; cp < ncopies; ++cp) {
-              mbar_wait(p.any_transform ? &readyA[sa] : &fullA[sa], pa);
+              const int slot = lt ? p.a_stages + sl : sa;
+              mbar_wait(p.any_transform ? &readyA[slot] : &fullA[slot], lt ? pl : pa);
               tc_fence_after();
-              uint32_t a_lo = umma_desc_lo(smem_u32(sA + sa * p.a_stage_bytes));
+              uint32_t a_lo = umma_desc_lo(smem_u32(lt ? sL + sl * p.l_stage_bytes : sA + sa * p.a_stage_bytes));
               int kx = 0;
               for (int tp = 0; tp < ntaps; ++tp) {
                 mbar_wait(&fullB[sb], pb);
@@ -340,8 +355,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
                 if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
                 if (++kx == 3) { kx = 0; a_lo += wrap16; } else { a_lo += step16; }
               }
-              if (elect_one()) umma_commit(&emptyA[sa]);
-              if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
+              if (elect_one()) umma_commit(&emptyA[slot]);
+              if (lt) {
+                if (++sl == p.l_stages) { sl = 0; pl ^= 1; }
+              } else {
+                if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
+              }
             }
           }
         }
@@ -356,8 +375,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
       const int tt = threadIdx.x - kWarpT * 32;
       const int jl = tt & 7;                  // logical 16B chunk = channels [jl*8, jl*8+8) of the 64-channel slab
       const int pl = tt >> 3;                 // pixel lane
-      int sa = 0;
-      uint32_t pa = 0;
+      int sa = 0, sl = 0;
+      uint32_t pa = 0, plt = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int mt = tile % p.m_tiles;
         const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, tn = mt / (p.tiles_x * p.tiles_y);
@@ -365,6 +384,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
         for (int e = 0; e < p.n_sched; ++e) {
           const int s = p.sched[e] >> 6, ch = p.sched[e] & 63;
           const ConvSegDev sg = p.seg[s];
+          const bool lt = p.l_stages != 0 && sg.mode == 0;
           const int ncopies = (sg.mode == 0 || sg.mode == 3) ? 1 : (sg.mode == 1 ? 3 : 9);
           const int pw = sg.mode == 3 ? p.TW + 2 : p.TW;      // pixels per (row, sample) in the stage
           const int prow = pw * p.NB;                          // pixels per tile row
@@ -383,9 +403,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
               }
             }
             for (int cp = 0; cp < ncopies; ++cp) {
-              mbar_wait_suspend(&fullA[sa], pa);
+              const int slot = lt ? p.a_stages + sl : sa;
+              mbar_wait_suspend(&fullA[slot], lt ? plt : pa);
               if (sg.affine != nullptr) {
-                uint8_t* stage = sA + sa * p.a_stage_bytes;
+                uint8_t* stage = lt ? sL + sl * p.l_stage_bytes : sA + sa * p.a_stage_bytes;
                 const int xoff = sg.mode == 3 ? -1 : (sg.mode == 1 ? cp - 1 : 0);
                 if (p.NB == 1) {
                   // 4 pixels in flight per thread: all shared-memory loads first, branch-free math, then the stores.
@@ -458,8 +479,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
                 fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
               }
               __syncwarp();
-              if (lane == 0) mbar_arrive(&readyA[sa]);
-              if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
+              if (lane == 0) mbar_arrive(&readyA[slot]);
+              if (lt) {
+                if (++sl == p.l_stages) { sl = 0; plt ^= 1; }
+              } else {
+                if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
+              }
             }
           }
         }
@@ -882,7 +907,9 @@ ASYRP_API int asyrp_conv_create(const AsyrpConvDesc* d, void** out_op) {
     if (rc != ASYRP_OK) { delete op; return rc; }
   }
   {
-    // K-loop schedule: heavy chunks (3x3 taps) in order, then the light chunks (1x1 segments)
+    // K-loop schedule.  Single activation ring: heavy chunks (3x3 taps) in order, then the light chunks (1x1
+    // segments).  Separate rings (halo tiles with 1x1 segments): the light chunks are spread evenly behind the heavy
+    // ones (H0 L0 L1 H1 L2 L3 ...), so that each pair of light slots is refilled during a heavy stage.
     uint8_t heavy[64], light[64];
     int nh = 0, nl = 0;
     for (int sg_ = 0; sg_ < d->nseg; ++sg_)
@@ -890,10 +917,11 @@ ASYRP_API int asyrp_conv_create(const AsyrpConvDesc* d, void** out_op) {
         ASYRP_REQUIRE(nh + nl < 64 && ch < 64, "asyrp_conv_create: more than 64 K chunks (%d channels) per tile", ktot);
         (p.seg[sg_].mode == 0 ? light[nl++] : heavy[nh++]) = static_cast<uint8_t>((sg_ << 6) | ch);
       }
+    const bool spread = halo && nl > 0 && nh > 0;
     int il = 0, n = 0;
     for (int ih = 0; ih < nh; ++ih) {
       p.sched[n++] = heavy[ih];
-      const int upto = (ih == nh - 1) ? nl : 0;  // light chunks after the last heavy chunk
+      const int upto = spread ? (nl * (ih + 1) + nh - 1) / nh : ((ih == nh - 1) ? nl : 0);
       while (il < upto) p.sched[n++] = light[il++];
     }
     while (il < nl) p.sched[n++] = light[il++];
@@ -914,13 +942,24 @@ ASYRP_API int asyrp_conv_create(const AsyrpConvDesc* d, void** out_op) {
   p.a_stage_bytes = halo ? (((THT + 2) * (p.TW + 2) * 128u + 1023u) / 1024u) * 1024u
                          : (any3 ? THT + 2 : THT) * p.row_bytes;
   const uint32_t b_stage = op->BN * 128;
-  // operand rings: ~200 KB of shared memory.  Activations: 3-4 stages; weights: as deep as fits (<= 16 stages) —
-  // small-N tiles issue an MMA group every ~100 cycles, so the weight prefetch must run many K steps ahead of the
-  // ~1 us TMA latency.
+  // operand rings: everything the 227 KB of shared memory leaves after barriers and the statistics scratch.
+  // Activations: 3-4 stages; weights: as deep as fits (<= 16 stages) — small-N tiles issue an MMA group every ~100
+  // cycles, so the weight prefetch must run many K steps ahead of the ~1 us TMA latency.
+  const uint32_t ring_budget = 227 * 1024 - 1024 /*alignment*/ - 1024 /*barriers*/ - 2 * 4 * op->BN * 4 /*stats*/;
+  bool has_light = false;
+  for (int s = 0; s < d->nseg; ++s) has_light = has_light || d->seg[s].mode == 0;
+  p.l_stages = 0;
+  p.l_stage_bytes = THT * p.row_bytes;
   p.a_stages = (p.MT == 2 || halo) ? 3 : 4;
-  const uint32_t ring_budget = 200 * 1024;
-  while (p.a_stages > 2 && p.a_stages * p.a_stage_bytes + 2 * b_stage > ring_budget) --p.a_stages;
-  int bs = static_cast<int>((ring_budget - p.a_stages * p.a_stage_bytes) / b_stage);
+  if (halo && has_light) {
+    // separate rings: 2 heavy slots (load + transform of one overlap the MMAs of the other; the light MMAs give the
+    // slack) + 2 light slots, if at least 3 weight stages still fit
+    const uint32_t need = 2 * p.a_stage_bytes + 2 * p.l_stage_bytes;
+    if (need + 3 * b_stage <= ring_budget) { p.a_stages = 2; p.l_stages = 2; }
+  }
+  const uint32_t a_ring = p.a_stages * p.a_stage_bytes + p.l_stages * p.l_stage_bytes;
+  while (p.l_stages == 0 && p.a_stages > 2 && p.a_stages * p.a_stage_bytes + 2 * b_stage > ring_budget) --p.a_stages;
+  int bs = static_cast<int>((ring_budget - (p.l_stages ? a_ring : p.a_stages * p.a_stage_bytes)) / b_stage);
   p.b_stages = bs > 16 ? 16 : (bs < 2 ? 2 : bs);
   p.ebias = d->ebias;
   p.ebias_stride = d->ebias_stride;
@@ -936,8 +975,8 @@ ASYRP_API int asyrp_conv_create(const AsyrpConvDesc* d, void** out_op) {
   p.out = static_cast<__half*>(d->out);
   p.stats = d->stats;
   op->smem_bytes = 1024 + static_cast<size_t>(p.a_stages) * p.a_stage_bytes +
-                   static_cast<size_t>(p.b_stages) * b_stage + (3 * p.a_stages + 2 * p.b_stages + 4) * 8 + 16 +
-                   2 * 4 * op->BN * 4;
+                   static_cast<size_t>(p.l_stages) * p.l_stage_bytes + static_cast<size_t>(p.b_stages) * b_stage +
+                   (3 * (p.a_stages + p.l_stages) + 2 * p.b_stages + 4) * 8 + 16 + 2 * 4 * op->BN * 4;
   ASYRP_REQUIRE(op->smem_bytes <= 227 * 1024, "asyrp_conv_create: smem %zu too large", op->smem_bytes);
   const int sms = sm_count();
   if (sms <= 0) { delete op; return ASYRP_ERR_NO_DEVICE; }
