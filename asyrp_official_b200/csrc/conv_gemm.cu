@@ -86,6 +86,45 @@ struct ConvParams {
   uint8_t sched[64];
 };
 
+// In-place operand transform of U pixels per thread (pixels px, px+lanes, ...; 8 threads per pixel, one 16-byte
+// chunk = 8 channels each) of a SWIZZLE_128B stage:  x -> act(a*x + b), out-of-image pixels -> 0 (the conv padding).
+template <int U>
+__device__ __forceinline__ void transform_pixels(uint8_t* stage, int px, int jl, int lanes, int npix, int& hy, int& r,
+                                                 int dhy, int dr, int prow, int xb, int yb, int W, int H, bool n_ok,
+                                                 const float (&ca)[8], const float (&cb)[8], int act) {
+  uint4 u[U];
+  bool ok[U], inimg[U];
+#pragma unroll
+  for (int k = 0; k < U; ++k) {
+    const int pk = px + k * lanes;
+    ok[k] = pk < npix;
+    const int x = xb + r, y = yb + hy;
+    inimg[k] = ok[k] && x >= 0 && x < W && y >= 0 && y < H && n_ok;
+    u[k] = make_uint4(0u, 0u, 0u, 0u);
+    if (ok[k]) u[k] = *reinterpret_cast<const uint4*>(stage + pk * 128 + ((jl ^ (pk & 7)) << 4));
+    hy += dhy;
+    r += dr;
+    if (r >= prow) { r -= prow; ++hy; }
+  }
+#pragma unroll
+  for (int k = 0; k < U; ++k) {
+    __half2* h2 = reinterpret_cast<__half2*>(&u[k]);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float2 f = __half22float2(h2[e]);
+      f.x = fmaf(ca[2 * e], f.x, cb[2 * e]);
+      f.y = fmaf(ca[2 * e + 1], f.y, cb[2 * e + 1]);
+      if (act) { f.x = silu_fast(f.x); f.y = silu_fast(f.y); }
+      h2[e] = inimg[k] ? __floats2half2_rn(f.x, f.y) : __floats2half2_rn(0.f, 0.f);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < U; ++k) {
+    const int pk = px + k * lanes;
+    if (ok[k]) *reinterpret_cast<uint4*>(stage + pk * 128 + ((jl ^ (pk & 7)) << 4)) = u[k];
+  }
+}
+
 // Swapped-operand epilogue of one warp: TMEM lane = output channel c, columns = the tile's pixels (row-major in the
 // TW x (MT*128/TW) tile); this warp drains the 32-pixel column chunks half, half+2, ...  TWS = log2(TW).
 template <int TWS, int MT>
@@ -307,7 +346,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
         const uint32_t d_tmem = tmem_base + acc * kAccCols;
         uint32_t accumulate = 0;
         for (int e = 0; e < p.n_sched; ++e) {
-          const int s = p.sched[e] >> 6, ch = p.sched[e] & 63;
+          const int s = p.sched[e] >> 6;
           const ConvSegDev sg = p.seg[s];
           const bool lt = p.l_stages != 0 && sg.mode == 0;
           const int ncopies = (sg.mode == 0 || sg.mode == 3) ? 1 : (sg.mode == 1 ? 3 : 9);
@@ -409,43 +448,25 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
                 uint8_t* stage = lt ? sL + sl * p.l_stage_bytes : sA + sa * p.a_stage_bytes;
                 const int xoff = sg.mode == 3 ? -1 : (sg.mode == 1 ? cp - 1 : 0);
                 if (p.NB == 1) {
-                  // 4 pixels in flight per thread: all shared-memory loads first, branch-free math, then the stores.
+                  // up to 4 pixels in flight per thread (all shared-memory loads first, branch-free math, then the
+                  // stores); the last groups of a stage use the 2- and 1-wide variants instead of idle lanes, since
+                  // the loop is bound by the SFU (two MUFU per element) and a 180-pixel halo tile is 1.4 passes.
                   // (hy, r) = (tile row, position inside the row) of pixel px, advanced incrementally (no divisions)
                   int hy = pl / prow, r = pl - hy * prow;
                   const int dhy = kLanes / prow, dr = kLanes - dhy * prow;
-                  for (int px = pl; px < npix; px += 4 * kLanes) {
-                    uint4 u[4];
-                    bool ok[4], inimg[4];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                      const int pk = px + k * kLanes;
-                      ok[k] = pk < npix;
-                      const int x = x0 + r + xoff, y = y0 + hy + yoff;
-                      inimg[k] = ok[k] && x >= 0 && x < p.W && y >= 0 && y < p.H && n0 < p.N;
-                      u[k] = make_uint4(0u, 0u, 0u, 0u);
-                      if (ok[k]) u[k] = *reinterpret_cast<const uint4*>(stage + pk * 128 + ((jl ^ (pk & 7)) << 4));
-                      hy += dhy;
-                      r += dr;
-                      if (r >= prow) { r -= prow; ++hy; }
-                    }
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                      __half2* h2 = reinterpret_cast<__half2*>(&u[k]);
-#pragma unroll
-                      for (int e = 0; e < 4; ++e) {
-                        float2 f = __half22float2(h2[e]);
-                        f.x = fmaf(ca[2 * e], f.x, cb[2 * e]);
-                        f.y = fmaf(ca[2 * e + 1], f.y, cb[2 * e + 1]);
-                        if (sg.act) { f.x = silu_fast(f.x); f.y = silu_fast(f.y); }
-                        h2[e] = inimg[k] ? __floats2half2_rn(f.x, f.y) : __floats2half2_rn(0.f, 0.f);
-                      }
-                    }
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                      const int pk = px + k * kLanes;
-                      if (ok[k]) *reinterpret_cast<uint4*>(stage + pk * 128 + ((jl ^ (pk & 7)) << 4)) = u[k];
-                    }
+                  const bool n_ok = n0 < p.N;
+                  int px = pl;
+                  for (; px - pl + 3 * kLanes < npix; px += 4 * kLanes)
+                    transform_pixels<4>(stage, px, jl, kLanes, npix, hy, r, dhy, dr, prow, x0 + xoff, y0 + yoff, p.W,
+                                        p.H, n_ok, ca, cb, sg.act);
+                  if (px - pl + kLanes < npix) {
+                    transform_pixels<2>(stage, px, jl, kLanes, npix, hy, r, dhy, dr, prow, x0 + xoff, y0 + yoff, p.W,
+                                        p.H, n_ok, ca, cb, sg.act);
+                    px += 2 * kLanes;
                   }
+                  if (px - pl < npix)
+                    transform_pixels<1>(stage, px, jl, kLanes, npix, hy, r, dhy, dr, prow, x0 + xoff, y0 + yoff, p.W,
+                                        p.H, n_ok, ca, cb, sg.act);
                 } else {
                   // tiles spanning several samples (layers below 16x16 when fused): per-pixel sample lookup
                   for (int px = pl; px < npix; px += kLanes) {

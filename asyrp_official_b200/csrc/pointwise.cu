@@ -22,17 +22,24 @@ __global__ void gn_finalize_kernel(const float* __restrict__ st_a, int Ca, int T
   const int C = Ca + Cb, cpg = C / 32;
   const int c_lo = g * cpg;
   double s = 0.0, ss = 0.0;
-  // pairs of this group in source a and b
-  const int pairs = cpg / 2;
-  for (int pi = 0; pi < pairs; ++pi) {
-    const int c = c_lo + pi * 2;
-    const float* base;
-    int T, Cs, cc;
-    if (c < Ca) { base = st_a; T = Ta; Cs = Ca; cc = c; }
-    else { base = st_b; T = Tb; Cs = Cb; cc = c - Ca; }
-    const float* pbase = base + (static_cast<size_t>(n) * T * (Cs / 2) + cc / 2) * 2;
-    for (int t = threadIdx.x; t < T; t += blockDim.x) {
-      const float2 v = *reinterpret_cast<const float2*>(pbase + static_cast<size_t>(t) * (Cs / 2) * 2);
+  // channel pairs of this group inside source a and inside source b (a group may straddle the seam); per source
+  // the (tile slot, pair) items are flattened so that consecutive threads read consecutive pairs of one slot
+  const int p_lo = c_lo / 2, p_hi = (c_lo + cpg) / 2;  // pair range on the concatenated axis
+  for (int src = 0; src < 2; ++src) {
+    const int Cs = src == 0 ? Ca : Cb, T = src == 0 ? Ta : Tb;
+    if (Cs == 0) continue;
+    const int off = src == 0 ? 0 : Ca / 2;
+    const int lo = (p_lo > off ? p_lo : off) - off;
+    const int hi = (p_hi < off + Cs / 2 ? p_hi : off + Cs / 2) - off;
+    const int np = hi - lo;
+    if (np <= 0) continue;
+    const float2* base = reinterpret_cast<const float2*>(src == 0 ? st_a : st_b) +
+                         static_cast<size_t>(n) * T * (Cs / 2) + lo;
+    const int items = np * T;
+#pragma unroll 4
+    for (int idx = threadIdx.x; idx < items; idx += blockDim.x) {
+      const int t = idx / np, pi = idx - t * np;
+      const float2 v = base[static_cast<size_t>(t) * (Cs / 2) + pi];
       s += v.x;
       ss += v.y;
     }
@@ -228,7 +235,8 @@ __global__ void timestep_embedding_kernel(const float* __restrict__ t, float* __
   }
 }
 
-// out[n][o] = bias[o] + sum_i W[o][i] * f(in[n][i]),  f = SiLU when act_in; one warp per (n, o)
+// out[n][o] = bias[o] + sum_i W[o][i] * f(in[n][i]),  f = SiLU when act_in.
+// Generic fallback: one warp per (n, o).
 __global__ void linear_kernel(const float* __restrict__ in, int in_stride, const float* __restrict__ Wt,
                               const float* __restrict__ bias, float* __restrict__ out, int out_stride, int N, int I,
                               int O, int act_in, int act_out) {
@@ -249,6 +257,53 @@ __global__ void linear_kernel(const float* __restrict__ in, int in_stride, const
     float r = acc + (bias ? bias[o] : 0.f);
     if (act_out) r = r / (1.0f + expf(-r));
     out[static_cast<size_t>(n) * out_stride + o] = r;
+  }
+}
+
+// Fast path (I = 32*KI): the block stages f(in) of up to `nc` samples in shared memory once, then each warp keeps
+// one weight row in registers and produces that output for all staged samples — the weight matrix (the 10-20 MB of
+// concatenated timestep-embedding projections) is read once instead of once per sample.  Per (n, o) the summation
+// order is the generic kernel's (lane-strided partial sums, xor-shuffle tree), so both give identical bits.
+constexpr int kLinOutPerWarp = 4;
+template <int KI>
+__global__ void __launch_bounds__(256) linear_rows_kernel(const float* __restrict__ in, int in_stride,
+                                                          const float* __restrict__ Wt, const float* __restrict__ bias,
+                                                          float* __restrict__ out, int out_stride, int N, int O,
+                                                          int nc, int act_in, int act_out) {
+  extern __shared__ float xs[];  // [nc][32*KI]
+  constexpr int I = 32 * KI;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int o0 = (blockIdx.x * 8 + warp) * kLinOutPerWarp;
+  for (int n0 = 0; n0 < N; n0 += nc) {
+    const int nn = N - n0 < nc ? N - n0 : nc;
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < nn * I; idx += 256) {
+      const int n = idx / I, i = idx - n * I;
+      float v = in[static_cast<size_t>(n0 + n) * in_stride + i];
+      if (act_in) v = v / (1.0f + expf(-v));
+      xs[idx] = v;
+    }
+    __syncthreads();
+    for (int oo = 0; oo < kLinOutPerWarp; ++oo) {
+      const int o = o0 + oo;
+      if (o >= O) break;
+      float w[KI];
+#pragma unroll
+      for (int k = 0; k < KI; ++k) w[k] = Wt[static_cast<size_t>(o) * I + lane + 32 * k];
+      const float b = bias ? bias[o] : 0.f;
+      for (int n = 0; n < nn; ++n) {
+        const float* x = xs + n * I + lane;
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < KI; ++k) acc += w[k] * x[32 * k];
+        for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+        if (lane == 0) {
+          float r = acc + b;
+          if (act_out) r = r / (1.0f + expf(-r));
+          out[static_cast<size_t>(n0 + n) * out_stride + o] = r;
+        }
+      }
+    }
   }
 }
 
@@ -406,7 +461,7 @@ ASYRP_API int asyrp_gn_finalize(const float* st_a, int Ca, int Ta, const float* 
   const int C = Ca + Cb;
   ASYRP_REQUIRE(C % 64 == 0, "asyrp_gn_finalize: C=%d must be a multiple of 64", C);
   const float count = static_cast<float>(HW) * (C / 32);
-  gn_finalize_kernel<<<dim3(32, N), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+  gn_finalize_kernel<<<dim3(32, N), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       st_a, Ca, Ta, st_b, Cb, Tb, gamma, beta, eps, count, scale_shift, ss_stride, affine);
   ASYRP_CHECK_CUDA(cudaGetLastError());
   return ASYRP_OK;
@@ -464,11 +519,25 @@ ASYRP_API int asyrp_timestep_embedding(const float* t, float* out, int N, int di
 
 ASYRP_API int asyrp_linear(const float* in, int in_stride, const float* W, const float* bias, float* out,
                            int out_stride, int N, int I, int O, int act_in, int act_out, void* stream) {
-  const size_t warps = static_cast<size_t>(N) * O;
-  const int block = 256;
-  const int grid = static_cast<int>((warps * 32 + block - 1) / block);
-  linear_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(in, in_stride, W, bias, out, out_stride, N,
-                                                                      I, O, act_in, act_out);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (I == 128 || I == 256 || I == 512 || I == 1024) {
+    int nc = (32 * 1024) / (I * 4);  // samples staged per pass: 32 KB of shared memory
+    if (nc > N) nc = N;
+    const int grid = (O + 8 * kLinOutPerWarp - 1) / (8 * kLinOutPerWarp);
+    const size_t smem = static_cast<size_t>(nc) * I * 4;
+#define ASYRP_LIN(KI_) \
+  linear_rows_kernel<KI_><<<grid, 256, smem, st>>>(in, in_stride, W, bias, out, out_stride, N, O, nc, act_in, act_out)
+    if (I == 128) ASYRP_LIN(4);
+    else if (I == 256) ASYRP_LIN(8);
+    else if (I == 512) ASYRP_LIN(16);
+    else ASYRP_LIN(32);
+#undef ASYRP_LIN
+  } else {
+    const size_t warps = static_cast<size_t>(N) * O;
+    const int block = 256;
+    const int grid = static_cast<int>((warps * 32 + block - 1) / block);
+    linear_kernel<<<grid, block, 0, st>>>(in, in_stride, W, bias, out, out_stride, N, I, O, act_in, act_out);
+  }
   ASYRP_CHECK_CUDA(cudaGetLastError());
   return ASYRP_OK;
 }
