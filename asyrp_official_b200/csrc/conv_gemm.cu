@@ -125,6 +125,41 @@ __device__ __forceinline__ void transform_pixels(uint8_t* stage, int px, int jl,
   }
 }
 
+// The same with everything per-pixel hoisted out: `base` already points at this thread's 16-byte chunk of its first
+// pixel (pixel lane * 128 B + swizzled chunk; pixel lanes are 32 apart = 4096 B, which leaves the swizzle phase
+// pk & 7 unchanged), bit k of `vld` / `img` says whether pixel k exists in the stage / lies inside the image.
+// CHK = false: every pixel exists and lies inside the image (all but the last group of an interior tile).
+template <int U, bool CHK>
+__device__ __forceinline__ void transform_fast(uint32_t base, uint32_t vld, uint32_t img, const float (&ca)[8],
+                                               const float (&cb)[8], int act) {
+  uint4 u[U];
+#pragma unroll
+  for (int k = 0; k < U; ++k) {
+    if (CHK) {
+      u[k] = make_uint4(0u, 0u, 0u, 0u);
+      if ((vld >> k) & 1u) u[k] = lds128(base + k * 4096);
+    } else {
+      u[k] = lds128(base + k * 4096);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < U; ++k) {
+    __half2* h2 = reinterpret_cast<__half2*>(&u[k]);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float2 f = __half22float2(h2[e]);
+      f.x = fmaf(ca[2 * e], f.x, cb[2 * e]);
+      f.y = fmaf(ca[2 * e + 1], f.y, cb[2 * e + 1]);
+      if (act) { f.x = silu_fast(f.x); f.y = silu_fast(f.y); }
+      h2[e] = __floats2half2_rn(f.x, f.y);
+    }
+    if (CHK && !((img >> k) & 1u)) u[k] = make_uint4(0u, 0u, 0u, 0u);
+  }
+#pragma unroll
+  for (int k = 0; k < U; ++k)
+    if (!CHK || ((vld >> k) & 1u)) sts128(base + k * 4096, u[k]);
+}
+
 // Swapped-operand epilogue of one warp: TMEM lane = output channel c, columns = the tile's pixels (row-major in the
 // TW x (MT*128/TW) tile); this warp drains the 32-pixel column chunks half, half+2, ...  TWS = log2(TW).
 template <int TWS, int MT>
@@ -414,6 +449,11 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
       const int tt = threadIdx.x - kWarpT * 32;
       const int jl = tt & 7;                  // logical 16B chunk = channels [jl*8, jl*8+8) of the 64-channel slab
       const int pl = tt >> 3;                 // pixel lane
+      const int toff = pl * 128 + ((jl ^ (pl & 7)) << 4);  // this thread's chunk of pixel `pl` inside a stage
+      // per-(tile, stage geometry) pixel masks of this thread: bit m = pixel pl + 32*m exists / lies inside the image
+      uint32_t m_vld = 0, m_img = 0;
+      int m_key = -1;
+      bool m_plain = false;
       int sa = 0, sl = 0;
       uint32_t pa = 0, plt = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -447,10 +487,44 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
               if (sg.affine != nullptr) {
                 uint8_t* stage = lt ? sL + sl * p.l_stage_bytes : sA + sa * p.a_stage_bytes;
                 const int xoff = sg.mode == 3 ? -1 : (sg.mode == 1 ? cp - 1 : 0);
-                if (p.NB == 1) {
-                  // up to 4 pixels in flight per thread (all shared-memory loads first, branch-free math, then the
-                  // stores); the last groups of a stage use the 2- and 1-wide variants instead of idle lanes, since
-                  // the loop is bound by the SFU (two MUFU per element) and a 180-pixel halo tile is 1.4 passes.
+                if (p.NB == 1 && (sg.mode == 3 || sg.mode == 0)) {
+                  // Up to 4 pixels in flight per thread (all shared-memory loads first, branch-free math, then the
+                  // stores); the last groups of a stage use the 2- and 1-wide variants instead of idle lanes (a
+                  // 180-pixel halo tile is 1.4 four-wide passes).  The pixel -> (row, column, in-image) bookkeeping
+                  // is done once per (tile, geometry) into two bit masks: the loop body was 25 % index arithmetic.
+                  const int key = tile * 4 + sg.mode;
+                  if (key != m_key) {
+                    m_key = key;
+                    m_vld = 0;
+                    m_img = 0;
+                    int hy = pl / prow, r = pl - hy * prow;
+                    const int dhy = kLanes / prow, dr = kLanes - dhy * prow;
+#pragma unroll 1
+                    for (int m = 0, pk = pl; pk < npix; ++m, pk += kLanes) {
+                      const int x = x0 + r + xoff, y = y0 + hy + yoff;
+                      m_vld |= 1u << m;
+                      if (x >= 0 && x < p.W && y >= 0 && y < p.H && n0 < p.N) m_img |= 1u << m;
+                      hy += dhy;
+                      r += dr;
+                      if (r >= prow) { r -= prow; ++hy; }
+                    }
+                    // warp-uniform: every existing pixel of every lane lies inside the image (interior tile)
+                    m_plain = __all_sync(0xffffffffu, m_img == m_vld);
+                  }
+                  const uint32_t tb = smem_u32(stage) + toff;
+                  const int ng = (npix + kLanes - 1) / kLanes;  // 32-pixel groups of the stage (<= 11)
+                  int m = 0;
+                  if (m_plain)  // interior tile: only the last group (partial) needs the masks
+                    for (; m + 4 < ng; m += 4) transform_fast<4, false>(tb + m * 4096, 0u, 0u, ca, cb, sg.act);
+                  for (; m + 4 <= ng; m += 4)
+                    transform_fast<4, true>(tb + m * 4096, m_vld >> m, m_img >> m, ca, cb, sg.act);
+                  if (m + 2 <= ng) {
+                    transform_fast<2, true>(tb + m * 4096, m_vld >> m, m_img >> m, ca, cb, sg.act);
+                    m += 2;
+                  }
+                  if (m < ng) transform_fast<1, true>(tb + m * 4096, m_vld >> m, m_img >> m, ca, cb, sg.act);
+                } else if (p.NB == 1) {
+                  // three dx-shifted copies (mode 1): the in-image test depends on the copy
                   // (hy, r) = (tile row, position inside the row) of pixel px, advanced incrementally (no divisions)
                   int hy = pl / prow, r = pl - hy * prow;
                   const int dhy = kLanes / prow, dr = kLanes - dhy * prow;
