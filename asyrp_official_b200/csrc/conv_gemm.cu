@@ -56,6 +56,9 @@ struct ConvParams {
   int TW, TH, NB;         // pixel sub-tile: TW x TH pixels of NB samples, TW*TH*NB == 128
   int MT;                 // sub-tiles (stacked in y) per CTA tile: 1 or 2; all share every weight tile
   int tiles_x, tiles_y, tiles_n, m_tiles, n_tiles;
+  // exact division by m_tiles / tiles_x / tiles_x*tiles_y as __umulhi(x, mul): mul = 2^32/d + 1, valid while
+  // x*d < 2^32 (checked at creation); d == 1 is encoded as mul == 0
+  uint32_t mul_m, mul_x, mul_xy;
   int a_stages, b_stages;
   uint32_t a_stage_bytes;  // ring slot size for A copies
   // Optional second activation ring for the 1x1 ("light") stages of a halo-tile conv.  A light stage is consumed in
@@ -85,6 +88,23 @@ struct ConvParams {
   int n_sched;
   uint8_t sched[64];
 };
+
+__device__ __forceinline__ int fast_div(int x, uint32_t mul) {
+  return mul ? static_cast<int>(__umulhi(static_cast<uint32_t>(x), mul)) : x;
+}
+// tile index -> (pixel tile column, row, sample-group, channel tile); a runtime integer division costs ~20
+// dependent instructions and every role needs these five at each tile start
+struct TileCoord { int mt, nt, tx, ty, tn; };
+__device__ __forceinline__ TileCoord tile_coord(const ConvParams& p, int tile) {
+  TileCoord c;
+  c.nt = fast_div(tile, p.mul_m);
+  c.mt = tile - c.nt * p.m_tiles;
+  c.tn = fast_div(c.mt, p.mul_xy);
+  const int rem = c.mt - c.tn * (p.tiles_x * p.tiles_y);
+  c.ty = fast_div(rem, p.mul_x);
+  c.tx = rem - c.ty * p.tiles_x;
+  return c;
+}
 
 // In-place operand transform of U pixels per thread (pixels px, px+lanes, ...; 8 threads per pixel, one 16-byte
 // chunk = 8 channels each) of a SWIZZLE_128B stage:  x -> act(a*x + b), out-of-image pixels -> 0 (the conv padding).
@@ -292,9 +312,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
       int sa = 0, sl = 0;      // heavy / light ring cursors
       uint32_t pa = 0, pl = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int mt = tile % p.m_tiles;
-        const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, tn = mt / (p.tiles_x * p.tiles_y);
-        const int x0 = tx * p.TW, y0 = ty * THT, n0 = tn * p.NB;
+        const TileCoord tc = tile_coord(p, tile);
+        const int x0 = tc.tx * p.TW, y0 = tc.ty * THT, n0 = tc.tn * p.NB;
         for (int e = 0; e < p.n_sched; ++e) {
           const int s = p.sched[e] >> 6, ch = p.sched[e] & 63;
           const ConvSegDev sg = p.seg[s];
@@ -338,8 +357,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
       int sb = 0;
       uint32_t pb = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int mt = tile % p.m_tiles, nt = tile / p.m_tiles;
-        const int tn = mt / (p.tiles_x * p.tiles_y);
+        const TileCoord tc = tile_coord(p, tile);
+        const int nt = tc.nt, tn = tc.tn;
         const int bz = p.b_batched ? tn * p.NB : 0;
         const int b_n = bz / p.b_heads, b_h = bz % p.b_heads;
         for (int e = 0; e < p.n_sched; ++e) {
@@ -450,16 +469,29 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
       const int jl = tt & 7;                  // logical 16B chunk = channels [jl*8, jl*8+8) of the 64-channel slab
       const int pl = tt >> 3;                 // pixel lane
       const int toff = pl * 128 + ((jl ^ (pl & 7)) << 4);  // this thread's chunk of pixel `pl` inside a stage
-      // per-(tile, stage geometry) pixel masks of this thread: bit m = pixel pl + 32*m exists / lies inside the image
-      uint32_t m_vld = 0, m_img = 0;
-      int m_key = -1;
-      bool m_plain = false;
+      // Pixel masks of this thread, bit m = pixel pl + 32*m.  Halo geometry ((TW+2) x (THT+2) pixels, tiles always
+      // whole): which pixels exist, and which sit in the left / right column or top / bottom row of the halo — those
+      // are outside the image exactly when the tile touches that image edge.  Plain geometry (1x1 stages): existence.
+      uint32_t h_vld = 0, h_l = 0, h_r = 0, h_t = 0, h_b = 0, d_vld = 0;
+      {
+        const int prow = p.TW + 2, rows = THT + 2;
+#pragma unroll 1
+        for (int m = 0, pk = pl; pk < rows * prow; ++m, pk += kLanes) {
+          const int hy = pk / prow, r = pk - hy * prow;
+          h_vld |= 1u << m;
+          if (r == 0) h_l |= 1u << m;
+          if (r == prow - 1) h_r |= 1u << m;
+          if (hy == 0) h_t |= 1u << m;
+          if (hy == rows - 1) h_b |= 1u << m;
+        }
+#pragma unroll 1
+        for (int m = 0, pk = pl; pk < THT * p.TW * p.NB; ++m, pk += kLanes) d_vld |= 1u << m;
+      }
       int sa = 0, sl = 0;
       uint32_t pa = 0, plt = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int mt = tile % p.m_tiles;
-        const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, tn = mt / (p.tiles_x * p.tiles_y);
-        const int x0 = tx * p.TW, y0 = ty * THT, n0 = tn * p.NB;
+        const TileCoord tc = tile_coord(p, tile);
+        const int x0 = tc.tx * p.TW, y0 = tc.ty * THT, n0 = tc.tn * p.NB;
         for (int e = 0; e < p.n_sched; ++e) {
           const int s = p.sched[e] >> 6, ch = p.sched[e] & 63;
           const ConvSegDev sg = p.seg[s];
@@ -487,29 +519,19 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
               if (sg.affine != nullptr) {
                 uint8_t* stage = lt ? sL + sl * p.l_stage_bytes : sA + sa * p.a_stage_bytes;
                 const int xoff = sg.mode == 3 ? -1 : (sg.mode == 1 ? cp - 1 : 0);
-                if (p.NB == 1 && (sg.mode == 3 || sg.mode == 0)) {
+                // whole tile inside the image (always true for halo tiles; 1x1 stages of ragged layers fall back)
+                const bool whole = x0 + p.TW <= p.W && y0 + THT <= p.H && n0 < p.N;
+                if (p.NB == 1 && whole && (sg.mode == 3 || sg.mode == 0)) {
                   // Up to 4 pixels in flight per thread (all shared-memory loads first, branch-free math, then the
                   // stores); the last groups of a stage use the 2- and 1-wide variants instead of idle lanes (a
-                  // 180-pixel halo tile is 1.4 four-wide passes).  The pixel -> (row, column, in-image) bookkeeping
-                  // is done once per (tile, geometry) into two bit masks: the loop body was 25 % index arithmetic.
-                  const int key = tile * 4 + sg.mode;
-                  if (key != m_key) {
-                    m_key = key;
-                    m_vld = 0;
-                    m_img = 0;
-                    int hy = pl / prow, r = pl - hy * prow;
-                    const int dhy = kLanes / prow, dr = kLanes - dhy * prow;
-#pragma unroll 1
-                    for (int m = 0, pk = pl; pk < npix; ++m, pk += kLanes) {
-                      const int x = x0 + r + xoff, y = y0 + hy + yoff;
-                      m_vld |= 1u << m;
-                      if (x >= 0 && x < p.W && y >= 0 && y < p.H && n0 < p.N) m_img |= 1u << m;
-                      hy += dhy;
-                      r += dr;
-                      if (r >= prow) { r -= prow; ++hy; }
-                    }
-                    // warp-uniform: every existing pixel of every lane lies inside the image (interior tile)
-                    m_plain = __all_sync(0xffffffffu, m_img == m_vld);
+                  // 180-pixel halo tile is 1.4 four-wide passes).  No per-pixel index arithmetic: see the masks above.
+                  uint32_t m_vld = d_vld, m_img = d_vld;
+                  bool m_plain = true;
+                  if (sg.mode == 3) {
+                    const bool el = x0 == 0, er = x0 + p.TW >= p.W, et = y0 == 0, eb = y0 + THT >= p.H;
+                    m_vld = h_vld;
+                    m_img = h_vld & ~((el ? h_l : 0u) | (er ? h_r : 0u) | (et ? h_t : 0u) | (eb ? h_b : 0u));
+                    m_plain = !(el || er || et || eb);
                   }
                   const uint32_t tb = smem_u32(stage) + toff;
                   const int ng = (npix + kLanes - 1) / kLanes;  // 32-pixel groups of the stage (<= 11)
@@ -599,11 +621,17 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int mt = tile % p.m_tiles, nt = tile / p.m_tiles;
-      const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, tn = mt / tiles_per_sample;
+      const TileCoord tc = tile_coord(p, tile);
+      const int nt = tc.nt, tx = tc.tx, ty = tc.ty, tn = tc.tn;
       const int x = tx * p.TW + xx, n = tn * p.NB + nn;
       const int tile_in_sample = ty * p.tiles_x + tx;
       float* st = s_stats + acc * (4 * BN);
+      // swapped variant: this thread's bias (+temb) value, fetched before the wait (a global-load latency per tile)
+      float eb_swap = 0.f;
+      if constexpr (SWAP) {
+        if (p.ebias != nullptr)
+          eb_swap = p.ebias[static_cast<size_t>(tn) * p.ebias_stride + nt * 128 + q * 32 + lane];
+      }
 
       mbar_wait_suspend(&tfull[acc], acc_phase);
       tc_fence_after();
@@ -612,8 +640,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
         // tile.  The swapped tile is only selected when it lies fully inside the image (conv_config), so there are
         // no bounds predicates here: this epilogue is instruction-issue bound (it set a ~9 us floor per tile).
         const int c = nt * 128 + q * 32 + lane;
-        const float eb = (p.ebias != nullptr ? p.ebias[static_cast<size_t>(tn) * p.ebias_stride + c] : 0.f) *
-                         p.acc_scale;
+        const float eb = eb_swap * p.acc_scale;
         const bool odd = (lane & 1) != 0;
         // lanes (2j, 2j+1) hold adjacent channels: the even lane stores pixel i, the odd lane pixel i+1, each as one
         // half2 (channel pair) -> a warp store covers two pixels x 64 B
@@ -939,6 +966,15 @@ ASYRP_API int asyrp_conv_create(const AsyrpConvDesc* d, void** out_op) {
   p.tiles_y = (d->H + THT - 1) / THT;
   p.tiles_n = (d->N + p.NB - 1) / p.NB;
   p.m_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
+  {
+    auto magic = [](uint32_t dv) -> uint32_t { return dv <= 1 ? 0u : static_cast<uint32_t>((1ull << 32) / dv) + 1u; };
+    p.mul_m = magic(p.m_tiles);
+    p.mul_x = magic(p.tiles_x);
+    p.mul_xy = magic(p.tiles_x * p.tiles_y);
+    const unsigned long long total = static_cast<unsigned long long>(p.m_tiles) * (d->Cout / 64);
+    ASYRP_REQUIRE(total * p.m_tiles < (1ull << 32), "asyrp_conv_create: %d pixel tiles exceed the tile-index range",
+                  p.m_tiles);
+  }
   p.n_tiles = d->Cout / op->BN;
   p.row_bytes = p.NB * p.TW * 128;
   p.nseg = d->nseg;
