@@ -12,14 +12,16 @@
 //
 // The K loop walks "segments": each segment is one source tensor (so a channel-concat input is two
 // segments and never materialised; a fused 1x1 shortcut is one more segment accumulated into the same
-// TMEM tile).  For a 3x3/s1 segment the producer loads, per 64-channel chunk, three dx-shifted copies of
-// the (TH+2)-row halo tile; the three dy taps of a copy are 1024B-aligned row offsets into it, so every
-// tap is a canonical K-major SWIZZLE_128B operand and TMA's out-of-bounds zero fill is the padding.
+// TMEM tile).  For a 3x3/s1 segment the producer loads, per 64-channel chunk, ONE (TH+2) x (8+2)-pixel halo tile
+// and the nine taps are start-address offsets into it (the 128B swizzle is a function of the shared-memory
+// address, the descriptor's stride-byte-offset is the halo pitch); layers narrower than 8x16 pixels use three
+// dx-shifted copies whose dy taps are 1024B-aligned row offsets.  TMA's out-of-bounds zero fill is the padding.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
-// warps 2..5 = epilogue (TMEM -> registers -> bias/residual -> fp16 NHWC store + GroupNorm partial sums).
-// Persistent: each CTA loops over output tiles (128 pixels x BN channels); two TMEM accumulators so the
-// epilogue of tile i overlaps the MMAs of tile i+1.
+// Warp roles (608 threads): warp 0 = activation TMA producer, warp 18 = weight TMA producer, warp 1 = TMEM allocator
+// + MMA issuer (all three: whole-warp uniform control flow, one elected lane issues), warps 2..9 = epilogue
+// (TMEM -> registers -> bias/residual -> fp16 NHWC store + GroupNorm partial sums), warps 10..17 = in-place operand
+// transform (fused GroupNorm-apply + SiLU).  Persistent: each CTA loops over output tiles; two TMEM accumulators
+// so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include "common.h"
 #include "ptx.cuh"
 #include <cstring>

@@ -48,6 +48,12 @@ def peaks():
     return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def burst_peak():
+    """best-of-10 single cuBLAS bf16 GEMM (the figure for a kernel timed alone); reported next to the sustained one"""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    return json.load(open(p)).get("bf16_tflops") if os.path.exists(p) else None
+
+
 class ClockSampler(threading.Thread):
     """SM clock / throttle reasons during the timed region (pynvml, 100 ms period)"""
 
@@ -262,6 +268,7 @@ def main():
         return
     # ---- per-kernel roofline of the dominant kernel (tcgen05 implicit-GEMM conv), per-launch CUDA events
     peak_tf, peak_gbs, peak_src = peaks()
+    burst_tf = burst_peak()
     P = eng.plan(batch)
     prof = P.profile(edit=True)
     by = {}
@@ -277,12 +284,13 @@ def main():
                 "gbs": round(d[2] / (d[0] * 1e-3) / 1e9, 1) if d[2] else None} for k, d in by.items()}
     roofline = {"bound": "tensor", "kernel": "conv_gemm_kernel (tcgen05 implicit GEMM, fp16 operands, fp32 accumulate)",
                 "achieved": round(conv_tf, 1), "peak": peak_tf, "unit": "TFLOP/s", "frac": round(conv_tf / peak_tf, 4),
-                # ncu --set full, 128->128 @256x256 launch of the same build (profiles/r1_final_conv_ncu_full.csv):
+                # ncu --set full, 128->128 @256x256 launch of the same build (profiles/r1_final2_conv_ncu_full.csv):
                 # dram__bytes_read.sum + dram__bytes_write.sum per launch, vs 537 MB algorithmic
-                "traffic": 495.1e6,
-                "traffic_note": "bytes per launch (dram read 268.8 MB + write 226.3 MB) of the 3x3 128->128 @256x256 "
-                                "batch-16 launch vs 536.9 MB algorithmic; profiles/r1_final_conv_ncu_full.csv",
+                "traffic": 496.1e6,
+                "traffic_note": "bytes per launch (dram read 268.9 MB + write 227.2 MB) of the 3x3 128->128 @256x256 "
+                                "batch-16 launch vs 536.9 MB algorithmic; profiles/r1_final2_conv_ncu_full.csv",
                 "peak_source": peak_src,
+                "frac_of_burst_peak": (round(conv_tf / burst_tf, 4) if burst_tf else None),
                 "how": f"sum of algorithmic conv FLOPs / sum of per-launch CUDA-event times over the {conv[3]} conv "
                        f"launches of one edit-step UNet evaluation (eager, same stream), batch {batch}",
                 "conv_share_of_step": round(conv[0] / tot_ms, 4),
