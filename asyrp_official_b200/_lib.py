@@ -35,6 +35,7 @@ class AsyrpConvDesc(C.Structure):
         ("stats", c_void_p),
         ("out_planar", c_void_p),
         ("planar_c", c_int),
+        ("up2", c_int),
     ]
 
 
@@ -42,6 +43,7 @@ class AsyrpConvDesc(C.Structure):
 SIGNATURES = {
     "asyrp_last_error": (C.c_char_p, []),
     "asyrp_conv_stats_tiles": (c_int, [c_int, c_int, c_int, c_int]),
+    "asyrp_conv_stats_tiles_up2": (c_int, [c_int, c_int, c_int]),
     "asyrp_conv_create": (c_int, [C.POINTER(AsyrpConvDesc), C.POINTER(c_void_p)]),
     "asyrp_conv_launch": (c_int, [c_void_p, c_void_p]),
     "asyrp_conv_set_scales": (c_int, [c_void_p, c_float, c_float]),

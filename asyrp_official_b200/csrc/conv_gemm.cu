@@ -86,6 +86,12 @@ struct ConvParams {
   int out_ld;              // elements between consecutive output pixels (Cout * out_heads)
   int out_f32;             // `out` is fp32 (attention logits keep fp32 precision for the softmax)
   int any_transform;       // some segment has an affine: the MMA warp then waits on readyA instead of fullA
+  // up2: this conv is "3x3 conv of the nearest-x2 upsampled input" (Upsample.conv, ddpm/diffusion.py:77-87) evaluated
+  // on the SOURCE image as four sub-pixel phases: output pixel (2i+a, 2j+b) only ever sees the 2x2 source
+  // neighbourhood rows {i-1+a, i+a} x cols {j-1+b, j+b}, with the 3x3 taps that fall on the same source pixel summed
+  // on the host.  N/H/W are the source geometry, the output is [N][2H][2W][Cout]; the channel-tile index carries the
+  // phase (n_tiles = 4 * Cout/BN, weight rows phase-major, K = 4*C): 4 of 9 tap MMAs, no upsampled tensor in HBM.
+  int up2;
   // K-loop order: entries (segment << 6 | 64-channel chunk), see asyrp_conv_create().
   int n_sched;
   uint8_t sched[64];
@@ -185,12 +191,13 @@ __device__ __forceinline__ void transform_fast(uint32_t base, uint32_t vld, uint
 // Swapped-operand epilogue of one warp: TMEM lane = output channel c, columns = the tile's pixels (row-major in the
 // TW x (MT*128/TW) tile); this warp drains the 32-pixel column chunks half, half+2, ...  TWS = log2(TW).
 template <int TWS, int MT>
-__device__ __forceinline__ void swap_epilogue(const ConvParams& p, uint32_t taddr, int half, int tn, int y0, int x0,
-                                              int c, int lane_off, uint32_t sel, float eb, float& s1, float& s2) {
+__device__ __forceinline__ void swap_epilogue(const ConvParams& p, uint32_t taddr, int half, size_t obase,
+                                              int row_stride, int cout, int lane_off, uint32_t sel, float eb,
+                                              float& s1, float& s2) {
+  // obase: element offset of the tile's first pixel at this lane's channel; row_stride / cout: elements between
+  // vertically / horizontally adjacent tile pixels in the output (doubled for the sub-pixel phases of an up2 conv)
   constexpr int TW = 1 << TWS;
   constexpr int kRows = 32 / TW;  // image rows per 32-pixel chunk
-  const int cout = p.Cout;
-  const int row_stride = p.W * cout;
   const float scale = p.acc_scale, rs = p.res_scale;
   const __half* __restrict__ resp = p.res;
   __half* __restrict__ outp = p.out;
@@ -198,8 +205,8 @@ __device__ __forceinline__ void swap_epilogue(const ConvParams& p, uint32_t tadd
   for (int cc = half; cc < (MT * 128) / 32; cc += 2) {
     uint32_t r[32];
     tmem_ld_32x32(taddr + cc * 32, r);
-    // element offset of the chunk's first pixel, channel c
-    const size_t o0 = ((static_cast<size_t>(tn) * p.H + y0 + cc * kRows) * p.W + x0) * cout + c;
+    // element offset of the chunk's first pixel
+    const size_t o0 = obase + static_cast<size_t>(cc * kRows) * row_stride;
     __half2 rv[16];
     if (resp != nullptr) {  // all residual loads first: independent of the stores below
       const __half* rp = resp + o0;
@@ -367,11 +374,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
           const int s = p.sched[e] >> 6, ch = p.sched[e] & 63;
           const ConvSegDev sg = p.seg[s];
           const int ncopies = (sg.mode == 0 || sg.mode == 3) ? 1 : (sg.mode == 1 ? 3 : 9);
-          const int ntaps = sg.mode == 1 ? 3 : (sg.mode == 3 ? 9 : 1);
+          const int ntaps = sg.mode == 1 ? 3 : (sg.mode == 3 ? (p.up2 ? 4 : 9) : 1);
           {
             for (int cp = 0; cp < ncopies; ++cp) {
               for (int tp = 0; tp < ntaps; ++tp) {
-                // tap index in the weight matrix: ky*3+kx
+                // tap index in the weight matrix: ky*3+kx (up2: dy*2+dx of the phase's 2x2 kernel; the weight rows
+                // nt*BN already select the phase)
                 const int tap = sg.mode == 0 ? 0 : (sg.mode == 1 ? tp * 3 + cp : (sg.mode == 3 ? tp : cp));
                 mbar_wait_suspend(&emptyB[sb], pb ^ 1);
                 if (elect_one()) {
@@ -400,13 +408,19 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
         mbar_wait_suspend(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * kAccCols;
+        int up_a = 0, up_b = 0;  // up2: sub-pixel phase of this tile = first tap (ky, kx) of its 2x2 kernel
+        if (p.up2) {
+          const int ph = fast_div(tile, p.mul_m) / (p.Cout / BN);
+          up_a = ph >> 1;
+          up_b = ph & 1;
+        }
         uint32_t accumulate = 0;
         for (int e = 0; e < p.n_sched; ++e) {
           const int s = p.sched[e] >> 6;
           const ConvSegDev sg = p.seg[s];
           const bool lt = p.l_stages != 0 && sg.mode == 0;
           const int ncopies = (sg.mode == 0 || sg.mode == 3) ? 1 : (sg.mode == 1 ? 3 : 9);
-          const int ntaps = sg.mode == 1 ? 3 : (sg.mode == 3 ? 9 : 1);
+          const int ntaps = sg.mode == 1 ? 3 : (sg.mode == 3 ? (p.up2 ? 4 : 9) : 1);
           // byte strides inside the A stage: between 8-row groups, between sub-tiles, per ky / kx tap step
           const uint32_t halo_pitch = (p.TW + 2) * 128u;
           const uint32_t sbo = sg.mode == 3 ? halo_pitch : 1024u;
@@ -416,14 +430,18 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
           const uint32_t sub16 = sub_stride >> 4;
           // tap step in 16-byte units.  mode 1: dy tap = row shift inside the dx copy; mode 3: (ky, kx) = pixel
           // offset inside the halo tile: +128 B per kx, and from kx=2 to the next ky row +halo_pitch-256 B
+          // (up2: 2x2 taps starting at (up_a, up_b): +128 B per kx, +halo_pitch-128 B to the next ky row)
           const uint32_t step16 = sg.mode == 3 ? 8u : (p.row_bytes >> 4);
-          const uint32_t wrap16 = sg.mode == 3 ? ((halo_pitch - 256u) >> 4) : step16;
+          const int kxn = p.up2 ? 2 : 3;
+          const uint32_t wrap16 = sg.mode == 3 ? ((halo_pitch - 128u * (kxn - 1)) >> 4) : step16;
+          const uint32_t first16 = (sg.mode == 3 && p.up2) ? ((up_a * halo_pitch + up_b * 128u) >> 4) : 0u;
           {
             for (int cp = 0; cp < ncopies; ++cp) {
               const int slot = lt ? p.a_stages + sl : sa;
               mbar_wait(p.any_transform ? &readyA[slot] : &fullA[slot], lt ? pl : pa);
               tc_fence_after();
-              uint32_t a_lo = umma_desc_lo(smem_u32(lt ? sL + sl * p.l_stage_bytes : sA + sa * p.a_stage_bytes));
+              uint32_t a_lo =
+                  umma_desc_lo(smem_u32(lt ? sL + sl * p.l_stage_bytes : sA + sa * p.a_stage_bytes)) + first16;
               int kx = 0;
               for (int tp = 0; tp < ntaps; ++tp) {
                 mbar_wait(&fullB[sb], pb);
@@ -448,7 +466,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
                 }
                 accumulate = 1;
                 if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
-                if (++kx == 3) { kx = 0; a_lo += wrap16; } else { a_lo += step16; }
+                if (++kx == kxn) { kx = 0; a_lo += wrap16; } else { a_lo += step16; }
               }
               if (elect_one()) umma_commit(&emptyA[slot]);
               if (lt) {
@@ -617,16 +635,24 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
     const int ep_tid = (warp - 2) * 32 + lane;
     const int row = q * 32 + lane;
     const int xx = row % p.TW, nn = (row / p.TW) % p.NB, yy = row / (p.TW * p.NB);
-    const int tiles_per_sample = p.tiles_x * p.tiles_y;
+    const int tiles_per_sample = p.tiles_x * p.tiles_y * (p.up2 ? 4 : 1);  // statistics slots per sample
     constexpr int kEpThreads = kNumEpilogueWarps * 32;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const TileCoord tc = tile_coord(p, tile);
-      const int nt = tc.nt, tx = tc.tx, ty = tc.ty, tn = tc.tn;
+      const int tx = tc.tx, ty = tc.ty, tn = tc.tn;
+      // up2: the channel-tile index carries the sub-pixel phase (a, b); outputs land on the (2H, 2W) grid
+      int nt = tc.nt, ph = 0;
+      if (p.up2) {
+        const int cts = p.Cout / BN;
+        ph = nt / cts;
+        nt -= ph * cts;
+      }
+      const int ps = p.up2 ? 2 : 1, OH = p.H * ps, OW = p.W * ps, pa = ph >> 1, pb = ph & 1;
       const int x = tx * p.TW + xx, n = tn * p.NB + nn;
-      const int tile_in_sample = ty * p.tiles_x + tx;
+      const int tile_in_sample = (ty * p.tiles_x + tx) * (p.up2 ? 4 : 1) + ph;
       float* st = s_stats + acc * (4 * BN);
       // swapped variant: this thread's bias (+temb) value, fetched before the wait (a global-load latency per tile)
       float eb_swap = 0.f;
@@ -647,14 +673,16 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
         // lanes (2j, 2j+1) hold adjacent channels: the even lane stores pixel i, the odd lane pixel i+1, each as one
         // half2 (channel pair) -> a warp store covers two pixels x 64 B
         const uint32_t sel = odd ? 0x3276u : 0x5410u;
-        const int lane_off = odd ? p.Cout - 1 : 0;
+        const int pix_stride = p.Cout * ps, row_stride = OW * pix_stride;
+        const int lane_off = odd ? pix_stride - 1 : 0;
+        const size_t obase = ((static_cast<size_t>(tn) * OH + ty * THT * ps + pa) * OW + tx * p.TW * ps + pb) * p.Cout + c;
         float s1 = 0.f, s2 = 0.f;
         if (p.TW == 8)
-          swap_epilogue<3, MT>(p, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kAccCols, half, tn,
-                               ty * THT, tx * 8, c, lane_off, sel, eb, s1, s2);
+          swap_epilogue<3, MT>(p, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kAccCols, half, obase,
+                               row_stride, pix_stride, lane_off, sel, eb, s1, s2);
         else
-          swap_epilogue<4, MT>(p, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kAccCols, half, tn,
-                               ty * THT, tx * 16, c, lane_off, sel, eb, s1, s2);
+          swap_epilogue<4, MT>(p, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kAccCols, half, obase,
+                               row_stride, pix_stride, lane_off, sel, eb, s1, s2);
         if (p.stats != nullptr) {
           // channel pair = lanes (2j, 2j+1); each (tile, half) owns one slot: nothing to reduce across warps
           s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
@@ -676,7 +704,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
           const int y = ty * THT + sub * p.TH + yy;
           const bool valid = (x < p.W) && (y < p.H) && (n < p.N);
           // output row of this pixel: batch entry n may be a (sample, head) pair writing a channel slice
-          const size_t pix = ((static_cast<size_t>(n / p.out_heads) * p.H + y) * p.W + x) * p.out_ld +
+          const size_t pix = ((static_cast<size_t>(n / p.out_heads) * OH + y * ps + pa) * OW + x * ps + pb) * p.out_ld +
                              static_cast<size_t>(n % p.out_heads) * p.Cout;
           uint32_t r[32];
           tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * (MT * BN) + sub * BN + cc * 32, r);
@@ -876,6 +904,7 @@ struct AsyrpConvDesc {
   float* stats;  // partial GroupNorm sums, see asyrp_conv_stats_tiles()
   float* out_planar;  // optional: fp32 NCHW [N][planar_c][H][W] receiving output channels [0, planar_c<=8)
   int planar_c;
+  int up2;  // 1: sub-pixel evaluation of conv3x3(nearest-x2 upsample(src)): see ConvParams::up2
 };
 
 static void conv_tile_shape(int H, int W, int halo, int* TW, int* TH, int* NB);
@@ -890,7 +919,7 @@ static int conv_halo_ok(int H, int W) { return H % 16 == 0 && W % 8 == 0; }
 // yields ~a full wave of tiles at a NOMINAL batch of 16, else the one with the most tiles.  The choice must not
 // depend on the actual batch: the tile partition fixes the summation order of the GroupNorm partial sums, and a
 // sample's result has to be bit-identical whatever batch (or batch shard on another GPU) it is part of.
-static void conv_config(int H, int W, int Cout, int halo, int* BN, int* MT) {
+static void conv_config(int H, int W, int Cout, int halo, int* BN, int* MT, int phases = 1) {
   int TW, TH, NB;
   conv_tile_shape(H, W, halo, &TW, &TH, &NB);
   constexpr int kNominalBatch = 16;
@@ -902,7 +931,7 @@ static void conv_config(int H, int W, int Cout, int halo, int* BN, int* MT) {
     if (Cout % bn != 0) continue;
     // two stacked sub-tiles: whole tiles only (the swapped-operand epilogue has no bounds predicates)
     if (mt == 2 && !(NB == 1 && H > 1 && H % (2 * TH) == 0 && W % TW == 0)) continue;
-    const int tiles = tiles_x * ((H + TH * mt - 1) / (TH * mt)) * tiles_n * (Cout / bn);
+    const int tiles = tiles_x * ((H + TH * mt - 1) / (TH * mt)) * tiles_n * (Cout / bn) * phases;
     if (tiles >= 120) { best = i; break; }
     if (tiles > best_tiles) { best = i; best_tiles = tiles; }
   }
@@ -946,6 +975,17 @@ ASYRP_API int asyrp_conv_stats_tiles(int H, int W, int Cout, int has_3x3) {
   return NB == 1 ? tiles : tiles * 4;
 }
 
+// statistics slots per sample written by an up2 conv over an H x W SOURCE image (output 2H x 2W)
+ASYRP_API int asyrp_conv_stats_tiles_up2(int H, int W, int Cout) {
+  int TW, TH, NB, bn, mt;
+  if (!conv_halo_ok(H, W)) return 0;
+  conv_tile_shape(H, W, 1, &TW, &TH, &NB);
+  conv_config(H, W, Cout, 1, &bn, &mt, 4);
+  const int tht = TH * mt;
+  const int tiles = ((W + TW - 1) / TW) * ((H + tht - 1) / tht) * 4;
+  return (bn == 128 && mt == 2) ? tiles * 2 : tiles;
+}
+
 ASYRP_API int asyrp_conv_create(const AsyrpConvDesc* d, void** out_op) {
   ASYRP_REQUIRE(d && out_op, "asyrp_conv_create: null argument");
   ASYRP_REQUIRE(d->nseg >= 1 && d->nseg <= kMaxSeg, "asyrp_conv_create: nseg=%d out of range", d->nseg);
@@ -961,7 +1001,12 @@ ASYRP_API int asyrp_conv_create(const AsyrpConvDesc* d, void** out_op) {
   ASYRP_REQUIRE(p.TW * p.TH * p.NB == 128, "asyrp_conv_create: cannot tile H=%d W=%d into 128 pixels", d->H,
                 d->W);
   ASYRP_REQUIRE(!(d->weight_batched && p.NB != 1), "asyrp_conv_create: batched weights need NB==1");
-  conv_config(d->H, d->W, d->Cout, halo, &op->BN, &op->MT);
+  if (d->up2)
+    ASYRP_REQUIRE(halo && d->nseg == 1 && d->seg[0].affine == nullptr && !d->weight_batched && !d->out_f32 &&
+                      d->out_planar == nullptr && d->out_heads <= 1 && d->a_heads <= 1 && d->residual == nullptr,
+                  "asyrp_conv_create: up2 needs one plain 3x3 segment on a source of H %% 16 == 0, W %% 8 == 0");
+  p.up2 = d->up2 ? 1 : 0;
+  conv_config(d->H, d->W, d->Cout, halo, &op->BN, &op->MT, p.up2 ? 4 : 1);
   p.MT = op->MT;
   const int THT = p.TH * p.MT;
   p.tiles_x = (d->W + p.TW - 1) / p.TW;
@@ -973,11 +1018,11 @@ ASYRP_API int asyrp_conv_create(const AsyrpConvDesc* d, void** out_op) {
     p.mul_m = magic(p.m_tiles);
     p.mul_x = magic(p.tiles_x);
     p.mul_xy = magic(p.tiles_x * p.tiles_y);
-    const unsigned long long total = static_cast<unsigned long long>(p.m_tiles) * (d->Cout / 64);
+    const unsigned long long total = static_cast<unsigned long long>(p.m_tiles) * (d->Cout / 64) * 4;
     ASYRP_REQUIRE(total * p.m_tiles < (1ull << 32), "asyrp_conv_create: %d pixel tiles exceed the tile-index range",
                   p.m_tiles);
   }
-  p.n_tiles = d->Cout / op->BN;
+  p.n_tiles = (d->Cout / op->BN) * (p.up2 ? 4 : 1);
   p.row_bytes = p.NB * p.TW * 128;
   p.nseg = d->nseg;
   bool any3 = false;
@@ -996,7 +1041,7 @@ ASYRP_API int asyrp_conv_create(const AsyrpConvDesc* d, void** out_op) {
     p.seg[s].act = sg.act;
     ASYRP_REQUIRE(!(sg.affine != nullptr && sg.mode == 2), "asyrp_conv_create: no fused affine on stride-2 segments");
     if (sg.affine != nullptr) p.any_transform = 1;
-    ktot += (sg.mode == 0 ? 1 : 9) * sg.C;
+    ktot += (sg.mode == 0 ? 1 : (p.up2 ? 4 : 9)) * sg.C;
     any3 = any3 || sg.mode == 1;
     uint64_t dims[5], strides[4];
     uint32_t box[5];
@@ -1025,7 +1070,7 @@ ASYRP_API int asyrp_conv_create(const AsyrpConvDesc* d, void** out_op) {
   }
   {
     const uint64_t bh = (d->weight_batched && d->b_heads > 1) ? d->b_heads : 1;
-    uint64_t dims[4] = {static_cast<uint64_t>(ktot), static_cast<uint64_t>(d->Cout), bh,
+    uint64_t dims[4] = {static_cast<uint64_t>(ktot), static_cast<uint64_t>(d->Cout) * (p.up2 ? 4 : 1), bh,
                         static_cast<uint64_t>(d->weight_batched ? d->N / bh : 1)};
     const uint64_t wld = d->weight_ld > 0 ? d->weight_ld : ktot;
     const uint64_t wbs = d->weight_batch_stride > 0 ? static_cast<uint64_t>(d->weight_batch_stride) : wld * d->Cout;

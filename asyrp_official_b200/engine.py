@@ -156,6 +156,8 @@ def pack_weights(arch: Arch, sd, device, n_delta):
     def resample(layer):
         p = layer.name
         W[p + ".w"], W[p + ".b"] = pk(sd[p + ".conv.weight"]), f32(sd[p + ".conv.bias"])
+        if layer.kind == "up":  # sub-pixel form of conv3x3(nearest-x2(x)): 4 phase kernels of 2x2 taps
+            W[p + ".w_up"] = ops.pack_upconv_weight(sd[p + ".conv.weight"].detach().float()).to(device)
 
     for stage in arch.enc + [arch.mid] + arch.dec:
         for layer in stage:
@@ -215,11 +217,12 @@ class Plan:
         """append one kernel launch; kind / algorithmic flops / algorithmic HBM bytes feed bench.py's roofline"""
         self._cur.append(Launch(fn, kind, flops, nbytes))
 
-    def _act(self, H, W, C, stats=False, has_3x3=False):
+    def _act(self, H, W, C, stats=False, has_3x3=False, tiles=None):
         t = self.pool.alloc((self.N, H, W, C), torch.float16)
         st = None
         if stats:
-            st = self.pool.alloc((self.N, ops.conv_stats_tiles(H, W, C, has_3x3), C // 2, 2), torch.float32)
+            tiles = tiles if tiles is not None else ops.conv_stats_tiles(H, W, C, has_3x3)
+            st = self.pool.alloc((self.N, tiles, C // 2, 2), torch.float32)
         return Act(t, st)
 
     def _free(self, act):
@@ -251,22 +254,25 @@ class Plan:
         return out
 
     def _conv(self, segs, weight, Cout, H, W, ebias=None, ebias_stride=0, residual=None, res_scale=1.0,
-              acc_scale=1.0, stats=True, planar=None, algo_flops=None):
+              acc_scale=1.0, stats=True, planar=None, algo_flops=None, up2=False):
+        """H, W: output geometry (for up2 = twice the source's)"""
         out = None
         if planar is None:
-            out = self._act(H, W, Cout, stats=stats, has_3x3=any(sg[1] == MODE_3x3 for sg in segs))
+            out = self._act(H, W, Cout, stats=stats, has_3x3=any(sg[1] == MODE_3x3 for sg in segs),
+                            tiles=ops.conv_stats_tiles_up2(H // 2, W // 2, Cout) if up2 else None)
         segs = [tuple(sg) + (None, 0, 0) * (len(sg) == 2) for sg in segs]
         op = ops.ConvOp([(sg[0].t,) + sg[1:] for sg in segs], weight, out=out.t if out else None, ebias=ebias,
                         ebias_stride=ebias_stride, residual=residual.t if residual is not None else None,
                         res_scale=res_scale, acc_scale=acc_scale, stats=out.stats if out else None,
-                        out_planar=planar, out_shape=(self.N, H, W, Cout))
+                        out_planar=planar, out_shape=(self.N, H, W, Cout), up2=up2)
         ktot = weight.shape[-1]
         flops = algo_flops if algo_flops is not None else 2.0 * self.N * H * W * Cout * ktot
         nbytes = 2.0 * (sum(sg[0].t.numel() for sg in segs) + weight.numel() + self.N * H * W * Cout
                         + (residual.t.numel() if residual is not None else 0))
         self._emit(op.launch, "conv", flops, nbytes)
-        self._cur[-1].desc = " + ".join(f"{'1x1 3x3 s2'.split()[sg[1]]}{'*' if sg[2] is not None else ''}:{sg[0].C}"
-                                        for sg in segs) + f" -> {Cout} @{H}x{W}"
+        self._cur[-1].desc = ("up2 " if up2 else "") + " + ".join(
+            f"{'1x1 3x3 s2'.split()[sg[1]]}{'*' if sg[2] is not None else ''}:{sg[0].C}" for sg in segs) + \
+            f" -> {Cout} @{H}x{W}"
         self._cur[-1].has_res = residual is not None
         return out, op
 
@@ -395,6 +401,11 @@ class Plan:
         p = layer.name
         if layer.kind == "down":
             out, _ = self._conv([(x, MODE_3x3_S2)], W[p + ".w"], layer.c, x.H // 2, x.W // 2, ebias=W[p + ".b"])
+            return out
+        if ops.conv_stats_tiles_up2(x.H, x.W, layer.c) > 0:
+            # Upsample.conv on the source image as four sub-pixel phases (4/9 of the MACs, nothing materialised);
+            # the launch's FLOPs are counted as executed, not as the reference's 9-tap count
+            out, _ = self._conv([(x, MODE_3x3)], W[p + ".w_up"], layer.c, 2 * x.H, 2 * x.W, ebias=W[p + ".b"], up2=True)
             return out
         up = self._apply([x], None, 0, RESAMPLE_UP2)
         out, _ = self._conv([(up, MODE_3x3)], W[p + ".w"], layer.c, up.H, up.W, ebias=W[p + ".b"])

@@ -39,8 +39,35 @@ def pack_conv_weight(w):
     return w.permute(0, 2, 3, 1).reshape(o, -1).to(torch.float16).contiguous()
 
 
+def pack_upconv_weight(w):
+    """Upsample.conv weights [O][I][3][3] -> sub-pixel form fp16 [4*O][4*I]: row (a*2+b)*O + o is the 2x2 kernel of
+    output phase (2i+a, 2j+b); column (dy*2+dx)*I + i multiplies source pixel (i-1+a+dy, j-1+b+dx).  The 3x3 taps that
+    land on the same source pixel under nearest-x2 upsampling are summed in fp32 before the fp16 rounding."""
+    w = w.float()
+    o, i = w.shape[:2]
+    groups = {0: ([0], [1, 2]), 1: ([0, 1], [2])}  # phase -> original tap indices per dy (dx)
+    rows = []
+    for a in (0, 1):
+        for b in (0, 1):
+            taps = []
+            for dy in (0, 1):
+                for dx in (0, 1):
+                    acc = torch.zeros(o, i, dtype=torch.float32, device=w.device)
+                    for ky in groups[a][dy]:
+                        for kx in groups[b][dx]:
+                            acc = acc + w[:, :, ky, kx]
+                    taps.append(acc)
+            rows.append(torch.stack(taps, 1).reshape(o, 4 * i))  # [O][4][I] -> tap-major, channel-minor
+    return torch.cat(rows, 0).to(torch.float16).contiguous()
+
+
 def conv_stats_tiles(H, W, C, has_3x3):
     return _lib.load().asyrp_conv_stats_tiles(H, W, C, int(has_3x3))
+
+
+def conv_stats_tiles_up2(H, W, C):
+    """slots per sample of the statistics an up2 conv over an H x W source writes (0: geometry unsupported)"""
+    return _lib.load().asyrp_conv_stats_tiles_up2(H, W, C)
 
 
 def new_stats(N, H, W, C, device, has_3x3):
@@ -60,7 +87,7 @@ class ConvOp:
 
     def __init__(self, segs, weight, out=None, ebias=None, ebias_stride=0, residual=None, res_scale=1.0,
                  acc_scale=1.0, stats=None, out_planar=None, out_shape=None, weight_batched=False, a_heads=1,
-                 b_heads=1, out_heads=1):
+                 b_heads=1, out_heads=1, up2=False):
         lib = _lib.load()
         segs = [tuple(sg) + (None, 0, 0) * (len(sg) == 2) for sg in segs]
         srcs = [sg[0] for sg in segs]
@@ -72,7 +99,11 @@ class ConvOp:
                 N, Cout = N * out_heads, Cout // out_heads
         else:
             N, H, W, Cout = out_shape
+        if up2:  # descriptor geometry = the source image; out is [N][2H][2W][Cout]
+            assert H % 2 == 0 and W % 2 == 0 and len(segs) == 1 and segs[0][1] == MODE_3x3
+            H, W = H // 2, W // 2
         d = AsyrpConvDesc()
+        d.up2 = int(up2)
         d.N, d.H, d.W, d.Cout = N, H, W, Cout
         d.nseg = len(segs)
         ktot = 0
@@ -91,10 +122,10 @@ class ConvOp:
                 d.seg[i].affine = aff.data_ptr() + aff_off * 2 * 4
                 d.seg[i].affine_stride = aff.shape[1] * 2
                 d.seg[i].act = int(act)
-            ktot += (1 if mode == MODE_1x1 else 9) * src.shape[-1]
+            ktot += (1 if mode == MODE_1x1 else (4 if up2 else 9)) * src.shape[-1]
         assert weight.dtype == torch.float16 and weight.stride(-1) == 1 and weight.shape[-1] == ktot, \
             (weight.shape, weight.stride(), ktot)
-        assert weight.shape[-2] == Cout
+        assert weight.shape[-2] == Cout * (4 if up2 else 1)
         d.weight = weight.data_ptr()
         d.weight_batched = int(weight_batched)
         d.weight_ld = weight.stride(-2)

@@ -83,11 +83,19 @@ typedef struct AsyrpConvDesc {
   float* stats;          /* [N][asyrp_conv_stats_tiles(..)][Cout/2][2] fp32 (sum, sum of squares) or NULL */
   float* out_planar;     /* optional fp32 NCHW [N][planar_c][H][W]: output channels [0, planar_c<=8) only */
   int planar_c;
+  /* up2 = 1: the op is Upsample.conv (models/ddpm/diffusion.py:77-87, improved_ddpm/unet.py:142-150), i.e.
+   * conv3x3(F.interpolate(src, scale_factor=2, mode="nearest")), evaluated on the SOURCE image as four sub-pixel
+   * phases: N/H/W are the source geometry (H%16==0, W%8==0), out is [N][2H][2W][Cout], one ASYRP_CONV_3x3 segment,
+   * weight is fp16 [4*Cout][4*C] (phase-major rows, 2x2 taps x C; the 3x3 taps that fall on one source pixel are
+   * pre-summed), stats has asyrp_conv_stats_tiles_up2() slots.  4/9 of the MACs, no upsampled tensor. */
+  int up2;
 } AsyrpConvDesc;
 
 /* number of tile slots of the stats buffer of a conv with this output geometry; has_3x3: the conv has an
  * ASYRP_CONV_3x3 segment (selects the 8x16 halo tile geometry when H%16==0 and W%8==0) */
 int asyrp_conv_stats_tiles(int H, int W, int Cout, int has_3x3);
+/* the same for an up2 conv over an H x W source image (0 if the geometry is unsupported) */
+int asyrp_conv_stats_tiles_up2(int H, int W, int Cout);
 int asyrp_conv_create(const AsyrpConvDesc* desc, void** op); /* encodes TMA descriptors; host only */
 int asyrp_conv_launch(void* op, void* stream);
 int asyrp_conv_set_scales(void* op, float acc_scale, float res_scale); /* hs_coeff of forward(), diffusion.py:512-516 */

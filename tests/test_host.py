@@ -184,3 +184,31 @@ def test_weight_packing_layout():
                         assert torch.equal(W[p + ".w1"][:, :9 * c0].float().reshape(layer.cout, 3, 3, c0),
                                            w[:, :c0].permute(0, 2, 3, 1).to(torch.float16).float())
         assert W["conv_in.w"].shape[1] == 9 * 64 and W["conv_out.w"].shape[0] == 64
+
+
+def test_upconv_subpixel_weights():
+    """pack_upconv_weight: conv3x3(nearest-x2(x)) == four 2x2 phase convs on x (reference: Upsample.forward,
+    models/ddpm/diffusion.py:77-87).  Checked in fp64 with the packed layout the kernel consumes."""
+    import torch.nn.functional as F
+    from asyrp_official_b200 import ops
+    torch.manual_seed(0)
+    n, ci, co, h, w = 2, 5, 3, 6, 4
+    x = torch.randn(n, ci, h, w, dtype=torch.float64)
+    wt = torch.randn(co, ci, 3, 3, dtype=torch.float64)
+    ref = F.conv2d(F.interpolate(x, scale_factor=2.0, mode="nearest"), wt, padding=1)
+    # packed rows: (a*2+b)*co + o ; columns: (dy*2+dx)*ci + i ; source pixel (y-1+a+dy, x-1+b+dx)
+    # (computed in fp32 by the packer; compare against an fp64 re-evaluation with a matching tolerance)
+    pk = ops.pack_upconv_weight(wt.float()).double().reshape(2, 2, co, 2, 2, ci)
+    xp = F.pad(x, (1, 1, 1, 1))
+    out = torch.zeros(n, co, 2 * h, 2 * w, dtype=torch.float64)
+    for a in (0, 1):
+        for b in (0, 1):
+            acc = torch.zeros(n, co, h, w, dtype=torch.float64)
+            for dy in (0, 1):
+                for dx in (0, 1):
+                    patch = xp[:, :, a + dy:a + dy + h, b + dx:b + dx + w]
+                    acc += torch.einsum("oi,nihw->nohw", pk[a, b, :, dy, dx, :], patch)
+            out[:, :, a::2, b::2] = acc
+    assert (out - ref).abs().max() < 2e-2 * ref.abs().max()  # fp16 rounding of the packed weights
+    pk32 = ops.pack_upconv_weight(wt.float())
+    assert pk32.shape == (4 * co, 4 * ci) and pk32.dtype == torch.float16

@@ -414,3 +414,32 @@ def test_multi_head_attention_gemms(cuda_device):
     torch.cuda.synchronize()
     o_ref = (P.double().cpu().reshape(N, heads, T, T) @ v).permute(0, 2, 1, 3).reshape(N, T, Cc)
     _check(O.float().cpu().reshape(N, T, Cc), o_ref, 1.5e-3, "multi-head P v")
+
+
+@pytest.mark.parametrize("N,H,W,C", [(2, 16, 16, 128), (1, 32, 24, 128), (2, 16, 16, 256), (17, 16, 8, 64),
+                                      (3, 64, 64, 128)])
+def test_upsample_conv_subpixel(cuda_device, N, H, W, C):
+    """Upsample.conv (ddpm/diffusion.py:77-87): conv3x3(F.interpolate(x, 2, 'nearest')) evaluated as four sub-pixel
+    phase convs on the source (AsyrpConvDesc.up2).  Reference: the plain formula on the fp16-rounded input with the
+    fp16-rounded PACKED (pre-summed) weights' fp32 originals — the pre-summing changes the rounding points, hence the
+    tolerance of a few fp16 ulps of the largest output."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(11)
+    x = _rand((N, C, H, W), g)
+    w = _rand((C, C, 3, 3), g, 1.0 / math.sqrt(9 * C))
+    eb = _rand((C,), g)
+    ref = F.conv2d(F.interpolate(_h(x), scale_factor=2.0, mode="nearest"), w.double(), padding=1) \
+        + eb.double()[None, :, None, None]
+    tiles = ops.conv_stats_tiles_up2(H, W, C)
+    assert tiles > 0
+    out = torch.zeros(N, 2 * H, 2 * W, C, dtype=torch.float16, device=cuda_device)
+    stats = torch.zeros(N, tiles, C // 2, 2, dtype=torch.float32, device=cuda_device)
+    op = ops.ConvOp([(_nhwc_half(x, cuda_device), ops.MODE_3x3)], ops.pack_upconv_weight(w).to(cuda_device), out=out,
+                    ebias=eb.to(cuda_device), stats=stats, up2=True)
+    op.launch()
+    op.launch()
+    torch.cuda.synchronize()
+    _check(_from_nhwc(out), ref, 2.5e-3, "up2 conv")
+    st = stats.sum(dim=1).cpu().double()
+    sref = _stats_ref(ref)
+    assert (st - sref).abs().max().item() <= 3e-3 * sref.abs().max().item() + 1e-3
