@@ -59,7 +59,7 @@ struct ConvParams {
   int MT;                 // sub-tiles (stacked in y) per CTA tile: 1 or 2; all share every weight tile
   int tiles_x, tiles_y, tiles_n, m_tiles, n_tiles;
   // exact division by m_tiles / tiles_x / tiles_x*tiles_y as __umulhi(x, mul): mul = 2^32/d + 1, valid while
-  // x*d < 2^32 (checked at creation); d == 1 is encoded as mul == 0
+  // x*d < 2^32; d == 1 is encoded as mul == 0, "range too large, divide in hardware" as mul == 1
   uint32_t mul_m, mul_x, mul_xy;
   int a_stages, b_stages;
   uint32_t a_stage_bytes;  // ring slot size for A copies
@@ -97,19 +97,20 @@ struct ConvParams {
   uint8_t sched[64];
 };
 
-__device__ __forceinline__ int fast_div(int x, uint32_t mul) {
-  return mul ? static_cast<int>(__umulhi(static_cast<uint32_t>(x), mul)) : x;
+__device__ __forceinline__ int fast_div(int x, uint32_t mul, int d) {
+  // mul == 0: d == 1; mul == 1: range too large for the 32-bit multiply-high (huge batches) -> hardware division
+  return mul > 1u ? static_cast<int>(__umulhi(static_cast<uint32_t>(x), mul)) : (mul == 0u ? x : x / d);
 }
 // tile index -> (pixel tile column, row, sample-group, channel tile); a runtime integer division costs ~20
 // dependent instructions and every role needs these five at each tile start
 struct TileCoord { int mt, nt, tx, ty, tn; };
 __device__ __forceinline__ TileCoord tile_coord(const ConvParams& p, int tile) {
   TileCoord c;
-  c.nt = fast_div(tile, p.mul_m);
+  c.nt = fast_div(tile, p.mul_m, p.m_tiles);
   c.mt = tile - c.nt * p.m_tiles;
-  c.tn = fast_div(c.mt, p.mul_xy);
+  c.tn = fast_div(c.mt, p.mul_xy, p.tiles_x * p.tiles_y);
   const int rem = c.mt - c.tn * (p.tiles_x * p.tiles_y);
-  c.ty = fast_div(rem, p.mul_x);
+  c.ty = fast_div(rem, p.mul_x, p.tiles_x);
   c.tx = rem - c.ty * p.tiles_x;
   return c;
 }
@@ -410,7 +411,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
         const uint32_t d_tmem = tmem_base + acc * kAccCols;
         int up_a = 0, up_b = 0;  // up2: sub-pixel phase of this tile = first tap (ky, kx) of its 2x2 kernel
         if (p.up2) {
-          const int ph = fast_div(tile, p.mul_m) / (p.Cout / BN);
+          const int ph = fast_div(tile, p.mul_m, p.m_tiles) / (p.Cout / BN);
           up_a = ph >> 1;
           up_b = ph & 1;
         }
@@ -1013,16 +1014,20 @@ ASYRP_API int asyrp_conv_create(const AsyrpConvDesc* d, void** out_op) {
   p.tiles_y = (d->H + THT - 1) / THT;
   p.tiles_n = (d->N + p.NB - 1) / p.NB;
   p.m_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
+  p.n_tiles = (d->Cout / op->BN) * (p.up2 ? 4 : 1);
   {
-    auto magic = [](uint32_t dv) -> uint32_t { return dv <= 1 ? 0u : static_cast<uint32_t>((1ull << 32) / dv) + 1u; };
+    // x / dv == umulhi(x, 2^32/dv + 1) for all x with x*dv < 2^32; the largest dividend is the tile count
+    const unsigned long long xmax = static_cast<unsigned long long>(p.m_tiles) * p.n_tiles;
+    auto magic = [xmax](uint32_t dv) -> uint32_t {
+      if (dv <= 1) return 0u;
+      if (xmax * dv >= (1ull << 32)) return 1u;
+      return static_cast<uint32_t>((1ull << 32) / dv) + 1u;
+    };
     p.mul_m = magic(p.m_tiles);
     p.mul_x = magic(p.tiles_x);
     p.mul_xy = magic(p.tiles_x * p.tiles_y);
-    const unsigned long long total = static_cast<unsigned long long>(p.m_tiles) * (d->Cout / 64) * 4;
-    ASYRP_REQUIRE(total * p.m_tiles < (1ull << 32), "asyrp_conv_create: %d pixel tiles exceed the tile-index range",
-                  p.m_tiles);
+    ASYRP_REQUIRE(xmax < (1ull << 31), "asyrp_conv_create: %llu tiles exceed the tile-index range", xmax);
   }
-  p.n_tiles = (d->Cout / op->BN) * (p.up2 ? 4 : 1);
   p.row_bytes = p.NB * p.TW * 128;
   p.nseg = d->nseg;
   bool any3 = false;
