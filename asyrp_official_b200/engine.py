@@ -42,10 +42,11 @@ class Act:
 
 
 class Launch:
-    __slots__ = ("fn", "kind", "flops", "nbytes", "desc", "has_res")
+    __slots__ = ("fn", "kind", "flops", "nbytes", "desc", "has_res", "exec_flops")
 
     def __init__(self, fn, kind, flops, nbytes):
         self.fn, self.kind, self.flops, self.nbytes, self.desc, self.has_res = fn, kind, flops, nbytes, kind, False
+        self.exec_flops = flops  # FLOPs the kernel issues; differs from the algorithmic count for sub-pixel up-convs
 
     def __call__(self):
         self.fn()
@@ -270,6 +271,7 @@ class Plan:
         nbytes = 2.0 * (sum(sg[0].t.numel() for sg in segs) + weight.numel() + self.N * H * W * Cout
                         + (residual.t.numel() if residual is not None else 0))
         self._emit(op.launch, "conv", flops, nbytes)
+        self._cur[-1].exec_flops = 2.0 * self.N * H * W * Cout * ktot if up2 else flops
         self._cur[-1].desc = ("up2 " if up2 else "") + " + ".join(
             f"{'1x1 3x3 s2'.split()[sg[1]]}{'*' if sg[2] is not None else ''}:{sg[0].C}" for sg in segs) + \
             f" -> {Cout} @{H}x{W}"
@@ -404,8 +406,9 @@ class Plan:
             return out
         if ops.conv_stats_tiles_up2(x.H, x.W, layer.c) > 0:
             # Upsample.conv on the source image as four sub-pixel phases (4/9 of the MACs, nothing materialised);
-            # the launch's FLOPs are counted as executed, not as the reference's 9-tap count
-            out, _ = self._conv([(x, MODE_3x3)], W[p + ".w_up"], layer.c, 2 * x.H, 2 * x.W, ebias=W[p + ".b"], up2=True)
+            # algorithmic FLOPs = the reference's 9-tap conv on the 2H x 2W image, executed = 4 taps
+            out, _ = self._conv([(x, MODE_3x3)], W[p + ".w_up"], layer.c, 2 * x.H, 2 * x.W, ebias=W[p + ".b"], up2=True,
+                                algo_flops=2.0 * self.N * 4 * x.H * x.W * layer.c * 9 * x.C)
             return out
         up = self._apply([x], None, 0, RESAMPLE_UP2)
         out, _ = self._conv([(up, MODE_3x3)], W[p + ".w"], layer.c, up.H, up.W, ebias=W[p + ".b"])

@@ -278,6 +278,7 @@ def main():
     tot_ms = sum(d[0] for d in by.values())
     conv = by["conv"]
     conv_tf = conv[1] / (conv[0] * 1e-3) / 1e12
+    conv_exec_tf = sum(L.exec_flops for L in P.launches(True) if L.kind == "conv") / (conv[0] * 1e-3) / 1e12
     step_tf = value / args.gpus * f_img(key, traj_steps, sch.n_edit) / 1e12
     kern = {k: {"ms": round(d[0], 3), "launches": d[3], "share": round(d[0] / tot_ms, 4),
                 "tflops": round(d[1] / (d[0] * 1e-3) / 1e12, 1) if d[1] else None,
@@ -291,6 +292,9 @@ def main():
                                 "batch-16 launch vs 536.9 MB algorithmic; profiles/r1_final2_conv_ncu_full.csv",
                 "peak_source": peak_src,
                 "frac_of_burst_peak": (round(conv_tf / burst_tf, 4) if burst_tf else None),
+                "executed_tflops": round(conv_exec_tf, 1),
+                "executed_note": "the five Upsample.conv launches issue 4/9 of their algorithmic MACs (sub-pixel "
+                                 "phases); every other conv launch executes exactly its algorithmic FLOPs",
                 "how": f"sum of algorithmic conv FLOPs / sum of per-launch CUDA-event times over the {conv[3]} conv "
                        f"launches of one edit-step UNet evaluation (eager, same stream), batch {batch}",
                 "conv_share_of_step": round(conv[0] / tot_ms, 4),
