@@ -36,12 +36,15 @@ class AsyrpConvDesc(C.Structure):
         ("out_planar", c_void_p),
         ("planar_c", c_int),
         ("up2", c_int),
+        ("scales", c_void_p),
     ]
 
 
 # name -> (restype, argtypes); every symbol include/asyrp_b200.h declares
 SIGNATURES = {
     "asyrp_last_error": (C.c_char_p, []),
+    "asyrp_set_pdl": (c_int, [c_int]),
+    "asyrp_get_pdl": (c_int, []),
     "asyrp_conv_stats_tiles": (c_int, [c_int, c_int, c_int, c_int]),
     "asyrp_conv_stats_tiles_up2": (c_int, [c_int, c_int, c_int]),
     "asyrp_conv_create": (c_int, [C.POINTER(AsyrpConvDesc), C.POINTER(c_void_p)]),

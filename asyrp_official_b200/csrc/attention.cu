@@ -14,6 +14,8 @@ namespace asyrp {
 template <int D>
 __global__ void __launch_bounds__(256) attention_kernel(const __half* __restrict__ qkv, __half* __restrict__ out,
                                                         int T, int heads, float scale) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int QT = 16, KT = 32, KS = D + 8;  // padded key row stride (halves): conflict-free 16B reads
   extern __shared__ __align__(16) uint8_t smem_attn[];
   __half* sq = reinterpret_cast<__half*>(smem_attn);  // [QT][D]
@@ -128,7 +130,7 @@ static int launch_attention(const void* qkv, void* out, int N, int T, int heads,
     attr_set = true;
   }
   dim3 grid((T + QT - 1) / QT, heads, N);
-  attention_kernel<D><<<grid, 256, smem, st>>>(static_cast<const __half*>(qkv), static_cast<__half*>(out), T, heads,
+  ASYRP_LAUNCH(attention_kernel<D>, dim3(grid), dim3(256), smem, st, static_cast<const __half*>(qkv), static_cast<__half*>(out), T, heads,
                                               scale);
   ASYRP_CHECK_CUDA(cudaGetLastError());
   return ASYRP_OK;
@@ -141,6 +143,8 @@ static int launch_attention(const void* qkv, void* out, int N, int T, int heads,
 // in: [N][T][ld] (C channels from `in`), out: [N][C][T]
 __global__ void __launch_bounds__(256) transpose_tc_kernel(const __half* __restrict__ in, __half* __restrict__ out,
                                                            int T, int C, int ld) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ __half tile[32][34];
   const int n = blockIdx.z, t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -154,6 +158,8 @@ __global__ void __launch_bounds__(256) transpose_tc_kernel(const __half* __restr
 // P[r][:] = softmax(scale * S[r][:]) over T columns, fp32 math (th.softmax(weight.float()), unet.py:393); one warp per row
 __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ S, __half* __restrict__ P,
                                                            int rows, int T, float scale) {
+  pdl_trigger();
+  pdl_wait();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= rows) return;
   const float* s = S + static_cast<size_t>(row) * T;
@@ -189,7 +195,7 @@ using namespace asyrp;
 extern "C" ASYRP_API int asyrp_transpose_tc(const void* in, void* out, int N, int T, int C, int ld, void* stream) {
   ASYRP_REQUIRE(C % 32 == 0, "asyrp_transpose_tc: C=%d must be a multiple of 32", C);
   dim3 grid((T + 31) / 32, C / 32, N);
-  transpose_tc_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __half*>(in),
+  ASYRP_LAUNCH(transpose_tc_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), static_cast<const __half*>(in),
                                                                            static_cast<__half*>(out), T, C, ld);
   ASYRP_CHECK_CUDA(cudaGetLastError());
   return ASYRP_OK;
@@ -197,7 +203,7 @@ extern "C" ASYRP_API int asyrp_transpose_tc(const void* in, void* out, int N, in
 
 extern "C" ASYRP_API int asyrp_softmax_rows(const void* S, void* P, long long rows, int T, float scale, void* stream) {
   ASYRP_REQUIRE(T >= 1 && T <= 1024, "asyrp_softmax_rows: T=%d out of range (<= 1024)", T);
-  softmax_rows_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  ASYRP_LAUNCH(softmax_rows_kernel, dim3(static_cast<unsigned>((rows + 7) / 8)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       static_cast<const float*>(S), static_cast<__half*>(P), static_cast<int>(rows), T, scale);
   ASYRP_CHECK_CUDA(cudaGetLastError());
   return ASYRP_OK;

@@ -1,5 +1,6 @@
 // Error string, driver entry points and device queries shared by libasyrp_b200.so.
 #include "common.h"
+#include <cstdlib>
 #include <mutex>
 
 namespace asyrp {
@@ -58,6 +59,8 @@ int encode_tensor_map(CUtensorMap* out, CUtensorMapDataType dt, uint32_t rank, c
   return ASYRP_OK;
 }
 
+void set_pdl(int on);
+
 int sm_count() {
   static int n = -1;
   if (n < 0) {
@@ -70,6 +73,21 @@ int sm_count() {
   return n;
 }
 
+static int g_pdl = -1;
+int pdl_enabled() {
+  if (g_pdl < 0) {
+    const char* e = getenv("ASYRP_PDL");
+    g_pdl = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return g_pdl;
+}
+void set_pdl(int on) { g_pdl = on ? 1 : 0; }
+
 }  // namespace asyrp
 
 extern "C" ASYRP_API const char* asyrp_last_error(void) { return asyrp::get_error(); }
+extern "C" ASYRP_API int asyrp_set_pdl(int enabled) {
+  asyrp::set_pdl(enabled);
+  return asyrp::ASYRP_OK;
+}
+extern "C" ASYRP_API int asyrp_get_pdl(void) { return asyrp::pdl_enabled(); }

@@ -39,6 +39,17 @@ const char* get_error();
     }                                       \
   } while (0)
 
+// kernel<<<grid, block, smem, stream>>>(args...) with the PDL launch attribute (see launch() below); returns
+// ASYRP_ERR_CUDA from the enclosing C-ABI function on failure
+#define ASYRP_LAUNCH(kernel, grid, block, smem, stream, ...)                                              \
+  do {                                                                                                    \
+    cudaError_t _le = ::asyrp::launch(kernel, grid, block, smem, stream, __VA_ARGS__);                    \
+    if (_le != cudaSuccess) {                                                                             \
+      ::asyrp::set_error("%s:%d: launch of %s failed: %s", __FILE__, __LINE__, #kernel, cudaGetErrorString(_le)); \
+      return ::asyrp::ASYRP_ERR_CUDA;                                                                     \
+    }                                                                                                     \
+  } while (0)
+
 // cuTensorMapEncodeTiled resolved at run time (no link-time dependency on libcuda, so the library loads
 // on a machine without a driver and simply fails loudly when an op is created).
 int encode_tensor_map(CUtensorMap* out, CUtensorMapDataType dt, uint32_t rank, const void* gaddr,
@@ -46,5 +57,31 @@ int encode_tensor_map(CUtensorMap* out, CUtensorMapDataType dt, uint32_t rank, c
                       CUtensorMapSwizzle swz);
 
 int sm_count();
+
+// Programmatic dependent launch (PDL).  Every kernel of the library starts with `griddepcontrol.launch_dependents`
+// and executes `griddepcontrol.wait` before its first global-memory access; launched with the
+// programmaticStreamSerialization attribute, kernel i+1 is scheduled (and runs its prologue: barrier init, TMEM
+// allocation, descriptor prefetch) while kernel i drains, instead of after it — inside a captured graph too.  The
+// ~300 launches of one UNet evaluation otherwise each pay the full launch gap.  asyrp_set_pdl(0) / ASYRP_PDL=0
+// restores plain stream-ordered launches.
+int pdl_enabled();
+
+template <typename... Exp, typename... Act>
+inline cudaError_t launch(void (*kernel)(Exp...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Act&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cfg.attrs = attr;
+  cfg.numAttrs = 0;
+  if (pdl_enabled()) {
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.numAttrs = 1;
+  }
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<Exp>(args)...);
+}
 
 }  // namespace asyrp

@@ -74,6 +74,9 @@ struct ConvParams {
   int ebias_stride;        // 0: one row shared by all samples
   const __half* res;       // residual, NHWC like out, or nullptr
   float res_scale, acc_scale;
+  // optional device-side copy of (acc_scale, res_scale): when set it overrides the two by-value fields, so that one
+  // captured CUDA graph serves every hs_coeff tuple (the DeltaBlock coefficients are per-call arguments of forward())
+  const float* scales;
   __half* out;             // [N][H][W][Cout] fp16, or nullptr when out_planar is used
   float* out_planar;       // optional fp32 planar [N][planar_c][H][W] holding output channels [0, planar_c)
   int planar_c;
@@ -194,12 +197,11 @@ __device__ __forceinline__ void transform_fast(uint32_t base, uint32_t vld, uint
 template <int TWS, int MT>
 __device__ __forceinline__ void swap_epilogue(const ConvParams& p, uint32_t taddr, int half, size_t obase,
                                               int row_stride, int cout, int lane_off, uint32_t sel, float eb,
-                                              float& s1, float& s2) {
+                                              float scale, float rs, float& s1, float& s2) {
   // obase: element offset of the tile's first pixel at this lane's channel; row_stride / cout: elements between
   // vertically / horizontally adjacent tile pixels in the output (doubled for the sub-pixel phases of an up2 conv)
   constexpr int TW = 1 << TWS;
   constexpr int kRows = 32 / TW;  // image rows per 32-pixel chunk
-  const float scale = p.acc_scale, rs = p.res_scale;
   const __half* __restrict__ resp = p.res;
   __half* __restrict__ outp = p.out;
 #pragma unroll 1
@@ -254,6 +256,7 @@ __device__ __forceinline__ void swap_epilogue(const ConvParams& p, uint32_t tadd
 // layers (70% of the FLOPs) stop being shared-memory-bandwidth bound.
 template <int BN, int MT, bool SWAP = false>
 __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvParams p) {
+  pdl_trigger();  // the next kernel of the stream may be scheduled as soon as every CTA of this grid is running
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B operands need 1024B alignment
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -310,6 +313,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the previous kernel's tail; from
+  // here on global memory written by it is read (and buffers it may still read are written)
+  pdl_wait();
 
   const int total_tiles = p.m_tiles * p.n_tiles;
 
@@ -638,6 +644,11 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
     const int xx = row % p.TW, nn = (row / p.TW) % p.NB, yy = row / (p.TW * p.NB);
     const int tiles_per_sample = p.tiles_x * p.tiles_y * (p.up2 ? 4 : 1);  // statistics slots per sample
     constexpr int kEpThreads = kNumEpilogueWarps * 32;
+    float acc_scale = p.acc_scale, res_scale = p.res_scale;
+    if (p.scales != nullptr) {
+      acc_scale = __ldg(p.scales);
+      res_scale = __ldg(p.scales + 1);
+    }
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -669,7 +680,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
         // tile.  The swapped tile is only selected when it lies fully inside the image (conv_config), so there are
         // no bounds predicates here: this epilogue is instruction-issue bound (it set a ~9 us floor per tile).
         const int c = nt * 128 + q * 32 + lane;
-        const float eb = eb_swap * p.acc_scale;
+        const float eb = eb_swap * acc_scale;
         const bool odd = (lane & 1) != 0;
         // lanes (2j, 2j+1) hold adjacent channels: the even lane stores pixel i, the odd lane pixel i+1, each as one
         // half2 (channel pair) -> a warp store covers two pixels x 64 B
@@ -680,10 +691,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
         float s1 = 0.f, s2 = 0.f;
         if (p.TW == 8)
           swap_epilogue<3, MT>(p, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kAccCols, half, obase,
-                               row_stride, pix_stride, lane_off, sel, eb, s1, s2);
+                               row_stride, pix_stride, lane_off, sel, eb, acc_scale, res_scale, s1, s2);
         else
           swap_epilogue<4, MT>(p, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kAccCols, half, obase,
-                               row_stride, pix_stride, lane_off, sel, eb, s1, s2);
+                               row_stride, pix_stride, lane_off, sel, eb, acc_scale, res_scale, s1, s2);
         if (p.stats != nullptr) {
           // channel pair = lanes (2j, 2j+1); each (tile, half) owns one slot: nothing to reduce across warps
           s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
@@ -721,9 +732,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
               v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
             }
           }
-          if (p.acc_scale != 1.0f) {
+          if (acc_scale != 1.0f) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] *= p.acc_scale;
+            for (int i = 0; i < 32; ++i) v[i] *= acc_scale;
           }
           if (p.res != nullptr && valid) {
             const uint4* rp = reinterpret_cast<const uint4*>(p.res + pix + c0);
@@ -734,8 +745,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
                 const float2 f = __half22float2(h2[k]);
-                v[j * 8 + k * 2] += p.res_scale * f.x;
-                v[j * 8 + k * 2 + 1] += p.res_scale * f.y;
+                v[j * 8 + k * 2] += res_scale * f.x;
+                v[j * 8 + k * 2 + 1] += res_scale * f.y;
               }
             }
           }
@@ -906,6 +917,7 @@ struct AsyrpConvDesc {
   float* out_planar;  // optional: fp32 NCHW [N][planar_c][H][W] receiving output channels [0, planar_c<=8)
   int planar_c;
   int up2;  // 1: sub-pixel evaluation of conv3x3(nearest-x2 upsample(src)): see ConvParams::up2
+  const float* scales;  // optional DEVICE pointer to (acc_scale, res_scale); overrides the two fields above at run time
 };
 
 static void conv_tile_shape(int H, int W, int halo, int* TW, int* TH, int* NB);
@@ -1155,6 +1167,7 @@ ASYRP_API int asyrp_conv_create(const AsyrpConvDesc* d, void** out_op) {
   p.res = static_cast<const __half*>(d->residual);
   p.res_scale = d->res_scale;
   p.acc_scale = d->acc_scale;
+  p.scales = d->scales;
   p.out = static_cast<__half*>(d->out);
   p.stats = d->stats;
   op->smem_bytes = 1024 + static_cast<size_t>(p.a_stages) * p.a_stage_bytes +
@@ -1181,8 +1194,19 @@ ASYRP_API int asyrp_conv_launch(void* handle, void* stream) {
   ConvOp* op = static_cast<ConvOp*>(handle);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   void* args[] = {&op->p};
-  ASYRP_CHECK_CUDA(cudaLaunchKernel(conv_kernel_ptr(op->BN, op->MT), dim3(op->grid), dim3(kNumThreads), args,
-                                    op->smem_bytes, st));
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  cfg.gridDim = dim3(op->grid);
+  cfg.blockDim = dim3(kNumThreads);
+  cfg.dynamicSmemBytes = op->smem_bytes;
+  cfg.stream = st;
+  cfg.attrs = attr;
+  if (pdl_enabled()) {
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.numAttrs = 1;
+  }
+  ASYRP_CHECK_CUDA(cudaLaunchKernelExC(&cfg, conv_kernel_ptr(op->BN, op->MT), args));
   return ASYRP_OK;
 }
 

@@ -18,6 +18,8 @@ __global__ void gn_finalize_kernel(const float* __restrict__ st_a, int Ca, int T
                                    int Cb, int Tb, const float* __restrict__ gamma, const float* __restrict__ beta,
                                    float eps, float count, const float* __restrict__ scale_shift, int ss_stride,
                                    float* __restrict__ affine) {
+  pdl_trigger();
+  pdl_wait();
   const int g = blockIdx.x, n = blockIdx.y;
   const int C = Ca + Cb, cpg = C / 32;
   const int c_lo = g * cpg;
@@ -120,6 +122,8 @@ __device__ __forceinline__ void store8(__half* p, const float (&f)[8]) {
 // pixels; consecutive threads cover consecutive octets of a pixel, so a warp reads/writes whole 128B+ lines.
 template <int RESAMPLE>
 __global__ void __launch_bounds__(256) apply_kernel(const ApplyParams p) {
+  pdl_trigger();
+  pdl_wait();
   const int C = p.Ca + p.Cb;
   const int octs = C >> 3;                 // octets per pixel
   const int lanes = blockDim.x / octs;     // pixels processed concurrently by a block (host guarantees octs | 256)
@@ -198,6 +202,8 @@ __global__ void __launch_bounds__(256) apply_kernel(const ApplyParams p) {
 // ---------------------------------------------------------------------------------------------
 __global__ void pack_input_kernel(const float* __restrict__ x, __half* __restrict__ out, int N, int Cin, int H,
                                   int W) {
+  pdl_trigger();
+  pdl_wait();
   const size_t total = static_cast<size_t>(N) * H * W * 8;  // 8 octets of 8 channels
   for (size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
        idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -221,6 +227,8 @@ __global__ void pack_input_kernel(const float* __restrict__ x, __half* __restric
 // ---------------------------------------------------------------------------------------------
 __global__ void timestep_embedding_kernel(const float* __restrict__ t, float* __restrict__ out, int N, int dim,
                                           int variant) {
+  pdl_trigger();
+  pdl_wait();
   const int half = dim / 2;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < N * half; idx += gridDim.x * blockDim.x) {
     const int n = idx / half, i = idx % half;
@@ -240,6 +248,8 @@ __global__ void timestep_embedding_kernel(const float* __restrict__ t, float* __
 __global__ void linear_kernel(const float* __restrict__ in, int in_stride, const float* __restrict__ Wt,
                               const float* __restrict__ bias, float* __restrict__ out, int out_stride, int N, int I,
                               int O, int act_in, int act_out) {
+  pdl_trigger();
+  pdl_wait();
   const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp_global >= N * O) return;
@@ -270,6 +280,8 @@ __global__ void __launch_bounds__(256) linear_rows_kernel(const float* __restric
                                                           const float* __restrict__ Wt, const float* __restrict__ bias,
                                                           float* __restrict__ out, int out_stride, int N, int O,
                                                           int nc, int act_in, int act_out) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float xs[];  // [nc][32*KI]
   constexpr int I = 32 * KI;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -317,6 +329,8 @@ __global__ void ddim_update_kernel(const float* __restrict__ x, const float* __r
                                    const float* __restrict__ em, const float* __restrict__ z,
                                    float* __restrict__ x_next, float* __restrict__ x0_out, int N, int Cx, int Ce,
                                    int HW, float at, float an, float c1, float c2, int use_z) {
+  pdl_trigger();
+  pdl_wait();
   const float sq1 = sqrtf(1.0f - at), sqa = sqrtf(at), sqn = sqrtf(an);
   const size_t total = static_cast<size_t>(N) * Cx * HW;
   for (size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
@@ -341,6 +355,8 @@ __global__ void ddim_update_kernel(const float* __restrict__ x, const float* __r
 __global__ void ddpm_update_kernel(const float* __restrict__ x, const float* __restrict__ et, const float* __restrict__ z,
                                    float* __restrict__ x_next, int N, int Cx, int Ce, int HW, float at, float bt,
                                    float logvar, int learned, float mask) {
+  pdl_trigger();
+  pdl_wait();
   const float weight = __fdiv_rn(bt, sqrtf(1.0f - at));
   const float inv = __fdiv_rn(1.0f, sqrtf(1.0f - bt));
   const size_t total = static_cast<size_t>(N) * Cx * HW;
@@ -357,6 +373,8 @@ __global__ void ddpm_update_kernel(const float* __restrict__ x, const float* __r
 // out = alpha*a + beta*b on fp16 tensors (fp32 math): h2 = c0*h + c_i*delta_h_i  (ddpm/diffusion.py:512-516)
 __global__ void axpby_kernel(const __half* __restrict__ a, const __half* __restrict__ b, __half* __restrict__ out,
                              float alpha, float beta, size_t n8) {
+  pdl_trigger();
+  pdl_wait();
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     float fa[8], fb[8], o[8];
@@ -370,6 +388,8 @@ __global__ void axpby_kernel(const __half* __restrict__ a, const __half* __restr
 
 // NHWC fp16 -> NCHW fp32 (API-visible copies of delta_h / middle_h)
 __global__ void unpack_nchw_kernel(const __half* __restrict__ in, float* __restrict__ out, int N, int C, int HW) {
+  pdl_trigger();
+  pdl_wait();
   const size_t total = static_cast<size_t>(N) * C * HW;
   for (size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
        idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -401,6 +421,8 @@ __global__ void __launch_bounds__(256) slerp_h_kernel(const __half* __restrict__
                                                       long long dh_stride, __half* __restrict__ h2,
                                                       float* __restrict__ stats, int T, int C, int H, int W, float t,
                                                       int use_mask) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float sh[8];
   const int n = blockIdx.x, HW = H * W;
   const __half* hn = h + static_cast<size_t>(n) * HW * C;
@@ -461,7 +483,7 @@ ASYRP_API int asyrp_gn_finalize(const float* st_a, int Ca, int Ta, const float* 
   const int C = Ca + Cb;
   ASYRP_REQUIRE(C % 64 == 0, "asyrp_gn_finalize: C=%d must be a multiple of 64", C);
   const float count = static_cast<float>(HW) * (C / 32);
-  gn_finalize_kernel<<<dim3(32, N), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  ASYRP_LAUNCH(gn_finalize_kernel, dim3(dim3(32, N)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       st_a, Ca, Ta, st_b, Cb, Tb, gamma, beta, eps, count, scale_shift, ss_stride, affine);
   ASYRP_CHECK_CUDA(cudaGetLastError());
   return ASYRP_OK;
@@ -492,9 +514,9 @@ ASYRP_API int asyrp_apply(const void* src_a, int Ca, const void* src_b, int Cb, 
   if (gx < 1) gx = 1;
   const dim3 grid(gx, N);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (resample == 0) apply_kernel<0><<<grid, threads, 0, st>>>(p);
-  else if (resample == 1) apply_kernel<1><<<grid, threads, 0, st>>>(p);
-  else apply_kernel<2><<<grid, threads, 0, st>>>(p);
+  if (resample == 0) ASYRP_LAUNCH(apply_kernel<0>, dim3(grid), dim3(threads), 0, st, p);
+  else if (resample == 1) ASYRP_LAUNCH(apply_kernel<1>, dim3(grid), dim3(threads), 0, st, p);
+  else ASYRP_LAUNCH(apply_kernel<2>, dim3(grid), dim3(threads), 0, st, p);
   ASYRP_CHECK_CUDA(cudaGetLastError());
   return ASYRP_OK;
 }
@@ -502,7 +524,7 @@ ASYRP_API int asyrp_apply(const void* src_a, int Ca, const void* src_b, int Cb, 
 ASYRP_API int asyrp_pack_input(const float* x, void* out, int N, int Cin, int H, int W, void* stream) {
   ASYRP_REQUIRE(Cin <= 64, "asyrp_pack_input: Cin=%d > 64", Cin);
   const size_t total = static_cast<size_t>(N) * H * W * 8;
-  pack_input_kernel<<<grid_for(total, 256, 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  ASYRP_LAUNCH(pack_input_kernel, dim3(grid_for(total, 256, 16)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       x, static_cast<__half*>(out), N, Cin, H, W);
   ASYRP_CHECK_CUDA(cudaGetLastError());
   return ASYRP_OK;
@@ -511,7 +533,7 @@ ASYRP_API int asyrp_pack_input(const float* x, void* out, int N, int Cin, int H,
 ASYRP_API int asyrp_timestep_embedding(const float* t, float* out, int N, int dim, int variant, void* stream) {
   ASYRP_REQUIRE(dim % 2 == 0, "asyrp_timestep_embedding: odd dim %d", dim);
   const int total = N * (dim / 2);
-  timestep_embedding_kernel<<<(total + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(t, out, N, dim,
+  ASYRP_LAUNCH(timestep_embedding_kernel, dim3((total + 127) / 128), dim3(128), 0, static_cast<cudaStream_t>(stream), t, out, N, dim,
                                                                                                variant);
   ASYRP_CHECK_CUDA(cudaGetLastError());
   return ASYRP_OK;
@@ -526,7 +548,7 @@ ASYRP_API int asyrp_linear(const float* in, int in_stride, const float* W, const
     const int grid = (O + 8 * kLinOutPerWarp - 1) / (8 * kLinOutPerWarp);
     const size_t smem = static_cast<size_t>(nc) * I * 4;
 #define ASYRP_LIN(KI_) \
-  linear_rows_kernel<KI_><<<grid, 256, smem, st>>>(in, in_stride, W, bias, out, out_stride, N, O, nc, act_in, act_out)
+  ASYRP_LAUNCH(linear_rows_kernel<KI_>, dim3(grid), dim3(256), smem, st, in, in_stride, W, bias, out, out_stride, N, O, nc, act_in, act_out)
     if (I == 128) ASYRP_LIN(4);
     else if (I == 256) ASYRP_LIN(8);
     else if (I == 512) ASYRP_LIN(16);
@@ -536,7 +558,7 @@ ASYRP_API int asyrp_linear(const float* in, int in_stride, const float* W, const
     const size_t warps = static_cast<size_t>(N) * O;
     const int block = 256;
     const int grid = static_cast<int>((warps * 32 + block - 1) / block);
-    linear_kernel<<<grid, block, 0, st>>>(in, in_stride, W, bias, out, out_stride, N, I, O, act_in, act_out);
+    ASYRP_LAUNCH(linear_kernel, dim3(grid), dim3(block), 0, st, in, in_stride, W, bias, out, out_stride, N, I, O, act_in, act_out);
   }
   ASYRP_CHECK_CUDA(cudaGetLastError());
   return ASYRP_OK;
@@ -546,7 +568,7 @@ ASYRP_API int asyrp_ddim_update(const float* x, const float* et, const float* em
                                 float* x0_out, int N, int Cx, int Ce, int HW, float at, float an, float c1, float c2,
                                 void* stream) {
   const size_t total = static_cast<size_t>(N) * Cx * HW;
-  ddim_update_kernel<<<grid_for(total, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  ASYRP_LAUNCH(ddim_update_kernel, dim3(grid_for(total, 256, 8)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       x, et, em, z, x_next, x0_out, N, Cx, Ce, HW, at, an, c1, c2, z != nullptr);
   ASYRP_CHECK_CUDA(cudaGetLastError());
   return ASYRP_OK;
@@ -556,7 +578,7 @@ ASYRP_API int asyrp_axpby(const void* a, const void* b, void* out, float alpha, 
                           void* stream) {
   ASYRP_REQUIRE(numel % 8 == 0, "asyrp_axpby: numel must be a multiple of 8");
   const size_t n8 = static_cast<size_t>(numel) / 8;
-  axpby_kernel<<<grid_for(n8, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  ASYRP_LAUNCH(axpby_kernel, dim3(grid_for(n8, 256, 8)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       static_cast<const __half*>(a), static_cast<const __half*>(b), static_cast<__half*>(out), alpha, beta, n8);
   ASYRP_CHECK_CUDA(cudaGetLastError());
   return ASYRP_OK;
@@ -564,7 +586,7 @@ ASYRP_API int asyrp_axpby(const void* a, const void* b, void* out, float alpha, 
 
 ASYRP_API int asyrp_unpack_nchw(const void* in, float* out, int N, int C, int HW, void* stream) {
   const size_t total = static_cast<size_t>(N) * C * HW;
-  unpack_nchw_kernel<<<grid_for(total, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  ASYRP_LAUNCH(unpack_nchw_kernel, dim3(grid_for(total, 256, 8)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       static_cast<const __half*>(in), out, N, C, HW);
   ASYRP_CHECK_CUDA(cudaGetLastError());
   return ASYRP_OK;
@@ -573,7 +595,7 @@ ASYRP_API int asyrp_unpack_nchw(const void* in, float* out, int N, int C, int HW
 ASYRP_API int asyrp_slerp_h(const void* h, const float* dh, long long dh_sample_stride, void* h2, float* stats,
                             int stats_tiles, int N, int C, int H, int W, float t, int use_mask, void* stream) {
   ASYRP_REQUIRE(C % 2 == 0 && stats_tiles >= 1, "asyrp_slerp_h: bad arguments");
-  slerp_h_kernel<<<N, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __half*>(h), dh, dh_sample_stride,
+  ASYRP_LAUNCH(slerp_h_kernel, dim3(N), dim3(256), 0, static_cast<cudaStream_t>(stream), static_cast<const __half*>(h), dh, dh_sample_stride,
                                                                     static_cast<__half*>(h2), stats, stats_tiles, C, H,
                                                                     W, t, use_mask);
   ASYRP_CHECK_CUDA(cudaGetLastError());
@@ -585,7 +607,7 @@ ASYRP_API int asyrp_ddpm_update(const float* x, const float* et, const float* z,
   ASYRP_REQUIRE(z != nullptr, "asyrp_ddpm_update: noise tensor required");
   ASYRP_REQUIRE(!learned_sigma || Ce >= 2 * Cx, "asyrp_ddpm_update: learned sigma needs 2*Cx model channels");
   const size_t total = static_cast<size_t>(N) * Cx * HW;
-  ddpm_update_kernel<<<grid_for(total, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  ASYRP_LAUNCH(ddpm_update_kernel, dim3(grid_for(total, 256, 8)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       x, et, z, x_next, N, Cx, Ce, HW, at, bt, logvar, learned_sigma, mask);
   ASYRP_CHECK_CUDA(cudaGetLastError());
   return ASYRP_OK;

@@ -215,6 +215,12 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16_m128(uint32_t n) {
   return (1u << 4) | (0u << 7) | (0u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// launch_dependents: the next kernel in the stream may be scheduled once every CTA of this grid has executed it;
+// wait: block until the preceding grid has completed and its memory operations are visible (no-op without PDL).
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---------------------------------------------------------------- misc
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");

@@ -207,8 +207,10 @@ class Plan:
         self.t = torch.zeros(N, dtype=torch.float32, device=dev)
         self.et = torch.zeros(N, a.out_ch, S, S, dtype=torch.float32, device=dev)
         self.et_mod = torch.zeros(N, a.out_ch, S, S, dtype=torch.float32, device=dev)
-        self.enc_ops, self.delta_ops, self.dec_ops, self.dec_mod_ops = [], [], [], []
-        self.scale_ops = []  # conv ops whose epilogue scales are hs_coeff
+        self.temb_ops, self.enc_ops, self.delta_ops, self.dec_ops, self.dec_mod_ops = [], [], [], [], []
+        # DeltaBlock coefficients (acc_scale, res_scale) of the h2 = c0*h + sum_i c_{i+1}*delta_h_i epilogues live in
+        # device memory: one captured graph serves every hs_coeff tuple
+        self.coef = torch.ones(max(eng.n_delta, 1), 2, dtype=torch.float32, device=dev)
         self._temps = []     # materialised operands to release after the next conv launch is recorded
         self._cur = self.enc_ops
         self._build()
@@ -255,7 +257,7 @@ class Plan:
         return out
 
     def _conv(self, segs, weight, Cout, H, W, ebias=None, ebias_stride=0, residual=None, res_scale=1.0,
-              acc_scale=1.0, stats=True, planar=None, algo_flops=None, up2=False):
+              acc_scale=1.0, stats=True, planar=None, algo_flops=None, up2=False, scales=None):
         """H, W: output geometry (for up2 = twice the source's)"""
         out = None
         if planar is None:
@@ -265,7 +267,7 @@ class Plan:
         op = ops.ConvOp([(sg[0].t,) + sg[1:] for sg in segs], weight, out=out.t if out else None, ebias=ebias,
                         ebias_stride=ebias_stride, residual=residual.t if residual is not None else None,
                         res_scale=res_scale, acc_scale=acc_scale, stats=out.stats if out else None,
-                        out_planar=planar, out_shape=(self.N, H, W, Cout), up2=up2)
+                        out_planar=planar, out_shape=(self.N, H, W, Cout), up2=up2, scales=scales)
         ktot = weight.shape[-1]
         flops = algo_flops if algo_flops is not None else 2.0 * self.N * H * W * Cout * ktot
         nbytes = 2.0 * (sum(sg[0].t.numel() for sg in segs) + weight.numel() + self.N * H * W * Cout
@@ -436,8 +438,9 @@ class Plan:
         eng, a, N, dev = self.eng, self.eng.arch, self.N, self.eng.device
         W = eng.W
         S = a.image_size
-        # ---- timestep embedding MLP + every per-block projection in one launch each
-        self._cur = self.enc_ops
+        # ---- timestep embedding MLP + every per-block projection in one launch each.  They depend on t only:
+        # sample() evaluates them once per schedule step before the loop (a table) and the graph copies one row per step
+        self._cur = self.temb_ops
         e0 = torch.zeros(N, a.base_ch, dtype=torch.float32, device=dev)
         e1 = torch.zeros(N, a.temb_ch, dtype=torch.float32, device=dev)
         self.temb = torch.zeros(N, a.temb_ch, dtype=torch.float32, device=dev)
@@ -450,6 +453,7 @@ class Plan:
         self._emit(lambda: ops.linear(self.temb, W["emb_cat.w"], W["emb_cat.b"], self.emb_all, act_in=True), "temb",
                    nbytes=4.0 * W["emb_cat.w"].numel())
         # ---- encoder
+        self._cur = self.enc_ops
         xin = self._act(S, S, 64, stats=False)
         self._emit(lambda: ops.pack_input(self.x, xin.t), "pack_input", nbytes=4.0 * self.x.numel() + 2.0 * xin.t.numel())
         first_ch = a.enc[1][0].cin
@@ -514,8 +518,8 @@ class Plan:
             dh, _ = self._conv(seg2, W[p + ".w2"], C, h.H, h.W, ebias=W[p + ".b2"], stats=False)
             self.delta_h = dh
         # h2 = c_{i+1} * (conv2(a2) + b2) + (c0*h | 1*h2_prev), with GroupNorm partial sums for the decoder
-        h2, op = self._conv(seg2, W[p + ".w2"], C, h.H, h.W, ebias=W[p + ".b2"], residual=h2_prev)
-        self.scale_ops.append((op, i))
+        h2, op = self._conv(seg2, W[p + ".w2"], C, h.H, h.W, ebias=W[p + ".b2"], residual=h2_prev,
+                            scales=self.coef[i])
         self.pool.release(aff)
         self._free(d1)
         self._drop_temps()
@@ -539,14 +543,19 @@ class Plan:
 
     # ------------------------------------------------------------------ execution
     def set_coeffs(self, hs_coeff):
-        if len(hs_coeff) < len(self.scale_ops) + 1:
+        """hs_coeff = (c0, c1, ..): DeltaBlock i's epilogue computes c_{i+1}*(conv + bias) + (c0 if i == 0 else 1)*prev;
+        written to device memory (stream-ordered), so it also takes effect for an already captured graph"""
+        n = self.eng.n_delta
+        if n == 0 or len(hs_coeff) < n + 1:
             return  # schedules without edit steps (origin pass, inversion) carry no DeltaBlock coefficients
-        for op, i in self.scale_ops:
-            op.set_scales(float(hs_coeff[i + 1]), float(hs_coeff[0]) if i == 0 else 1.0)
+        host = torch.tensor([[float(hs_coeff[i + 1]), float(hs_coeff[0]) if i == 0 else 1.0] for i in range(n)],
+                            dtype=torch.float32)
+        self.coef.copy_(host, non_blocking=False)
 
-    def launches(self, edit):
+    def launches(self, edit, temb=True):
         """kernel launches of one UNet evaluation"""
-        ops_ = self.enc_ops + (self.delta_ops + self.dec_mod_ops if edit else []) + self.dec_ops
+        ops_ = (self.temb_ops if temb else []) + self.enc_ops + (self.delta_ops + self.dec_mod_ops if edit else []) \
+            + self.dec_ops
         return ops_
 
     def profile(self, edit=True, reps=3):
@@ -567,9 +576,37 @@ class Plan:
                 best[i] = min(best[i], e0.elapsed_time(e1))
         return [(L.kind, ms, L.flops, L.nbytes) for L, ms in zip(seq, best)]
 
+    def run_temb(self):
+        for f in self.temb_ops:
+            f()
+
     def run_encoder(self):
         for f in self.enc_ops:
             f()
+
+    def graph_time(self, launches, reps=20, warm=5):
+        """average device time (ms) of one pass over `launches`, captured as a CUDA graph and replayed back to back:
+        the launch gaps, clocks and power state of the real trajectory graph rather than eager per-launch events"""
+        st = torch.cuda.Stream(device=self.eng.device)
+        st.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(st):
+            for L in launches:
+                L()
+        torch.cuda.current_stream().wait_stream(st)
+        torch.cuda.synchronize(self.eng.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for L in launches:
+                L()
+        for _ in range(warm):
+            g.replay()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize(self.eng.device)
+        return e0.elapsed_time(e1) / reps
 
     def run_edit(self, explicit=False):
         for f in (self.slerp_ops if explicit else self.delta_ops):
@@ -617,6 +654,7 @@ class UNetEngine:
             if index is not None and index + 1 > self.n_delta and edit and not explicit:
                 raise ops._lib.AsyrpError(f"index={index} needs {index + 1} DeltaBlocks; engine packed {self.n_delta}")
             self.state["ignore_timestep"] = bool(ignore_timestep)
+            P.run_temb()
             P.run_encoder()
             delta = None
             if edit and explicit:
@@ -646,62 +684,125 @@ class UNetEngine:
             return et, et_mod, delta, P.mid_f32.clone()
 
     # ---- whole trajectory --------------------------------------------------------------------------
-    def sample(self, x_T, schedule, noise=None, use_graph=True, out=None):
+    MAX_GRAPHS = 4  # captured trajectory graphs kept per engine (least recently used is dropped)
+
+    def _build_trajectory(self, P, schedule, use_graph, explicit, record_dh, record_process):
+        """per-(batch, schedule) state: the timestep-embedding table, the noise buffer, the step loop and its graph"""
+        steps = schedule.steps
+        n_sto = schedule.n_stochastic
+        zbuf = torch.zeros((max(n_sto, 1), *P.x.shape), dtype=torch.float32, device=self.device)
+        # timestep MLP + every per-block projection depend on t only: evaluate them once per step here (4 launches
+        # each, outside the graph); inside the graph a step just copies its row into the buffer the convs read
+        emb_table = torch.empty((len(steps), *P.emb_all.shape), dtype=torch.float32, device=self.device)
+        for k, s in enumerate(steps):
+            P.t.fill_(float(s.t))
+            P.run_temb()
+            emb_table[k].copy_(P.emb_all)
+        learned_sigma = self.arch.out_ch == 2 * self.arch.in_ch
+
+        def is_edit(s):  # 'ddpm' steps use e_t only (utils/diffusion_utils.py:74-82): the edit pass cannot change x
+            return s.edit and s.kind == "ddim" and (explicit or self.n_delta > 0)
+
+        n_edit = sum(1 for s in steps if is_edit(s))
+        rec = {}
+        if explicit:   # per-edit-step explicit delta_h rows (raw-Δh checkpoints / mean Δh), filled before each replay
+            rec["dh_in"] = torch.zeros((max(n_edit, 1), *P.dh_user.shape), dtype=torch.float32, device=self.device)
+        if record_dh:  # DeltaBlock outputs per edit step (get_delta_hs, diffusion_latent.py:528-532)
+            rec["delta_h"] = torch.zeros((max(n_edit, 1), *P.delta_f32.shape), dtype=torch.float32, device=self.device)
+        if record_process:  # x_t and x0_t after every step (save_process_*, :485-491,523-527)
+            rec["x"] = torch.zeros((len(steps), *P.x.shape), dtype=torch.float32, device=self.device)
+            rec["x0_t"] = torch.zeros((len(steps), *P.x.shape), dtype=torch.float32, device=self.device)
+
+        def body():
+            zi = ei = 0
+            for k, s in enumerate(steps):
+                P.emb_all.copy_(emb_table[k])
+                P.run_encoder()
+                edit = is_edit(s)
+                if edit:
+                    if explicit:
+                        P.dh_user.copy_(rec["dh_in"][ei])
+                    P.run_edit(explicit=explicit)
+                    if record_dh:
+                        ops.unpack_nchw(P.delta_h.t, rec["delta_h"][ei])
+                    ei += 1
+                P.run_decoder()
+                z = None
+                if s.stochastic:
+                    z = zbuf[zi]
+                    zi += 1
+                if s.kind == "ddpm":
+                    ops.ddpm_update(P.x, P.et, z, P.x, s.at, s.bt, s.logvar, learned_sigma, s.mask)
+                else:
+                    ops.ddim_update(P.x, P.et, P.et_mod if edit else P.et, z, P.x,
+                                    rec["x0_t"][k] if record_process else None, s.at, s.an, s.c1, s.c2)
+                if record_process:
+                    rec["x"][k].copy_(P.x)
+
+        n_launch = sum(len(P.launches(False, temb=False)) + 1 for s in steps)
+        n_launch += n_edit * ((len(P.slerp_ops) if explicit else len(P.delta_ops)) + len(P.dec_mod_ops) + int(record_dh))
+        g = {"zbuf": zbuf, "emb_table": emb_table, "body": body, "graph": None, "launches": n_launch, "rec": rec,
+             "n_edit": n_edit}
+        if use_graph:
+            s_ = torch.cuda.Stream(device=self.device)
+            s_.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s_):
+                # warm-up launch outside capture (lazy function attributes, first-touch)
+                P.emb_all.copy_(emb_table[0])
+                P.run_encoder()
+                if explicit or self.n_delta:
+                    P.run_edit(explicit=explicit)
+                P.run_decoder()
+            torch.cuda.current_stream().wait_stream(s_)
+            torch.cuda.synchronize(self.device)
+            cg = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(cg):
+                body()
+            g["graph"] = cg
+        return g
+
+    def sample(self, x_T, schedule, noise=None, use_graph=True, out=None, delta_hs=None, use_mask=False,
+               record_dh=False, record_process=False):
         """Run the reverse trajectory of `schedule` (sampler.Schedule) from x_T; returns x_0 (fp32 NCHW).
 
-        The step list, the edit/plain/stochastic phase of every step and all coefficients are host-side integers /
-        floats fixed before launch, so the whole loop is one CUDA graph: per step a t-table copy, the UNet kernels,
-        and the fused DDIM update that writes x_t in place.  noise: [n_stochastic_steps][N][C][H][W] (pre-drawn)."""
+        The step list, the edit/plain/stochastic phase of every step and all sampler coefficients are host-side
+        integers / floats fixed before launch, so the whole loop is one CUDA graph: per step a copy of the step's
+        timestep-embedding row, the UNet kernels, and the fused DDIM (or ancestral 'ddpm') update that writes x_t in
+        place.  The DeltaBlock coefficients hs_coeff are device-side values: every coefficient tuple replays the same
+        graph.  noise: [n_stochastic_steps][N][C][H][W] (pre-drawn N(0,1)).
+
+        delta_hs: explicit Δh for the edit steps, [n_edit][C][h][w] (or [n_edit][N][C][h][w]) — the reference's
+        forward(delta_h=...) branch: h2 = slerp(1 - hs_coeff[0], h, |h| Δh/|Δh|) (ddpm/diffusion.py:518-539).
+        record_dh / record_process: keep the DeltaBlock output of every edit step / (x_t, x0_t) of every step in
+        `self.last_records` (device tensors owned by the cached trajectory; clone before the next call)."""
         N = x_T.shape[0]
         P = self.plan(N)
-        key = (N, schedule.key())
+        explicit = delta_hs is not None
+        slerp_t = 1.0 - float(schedule.hs_coeff[0]) if explicit else 0.0
+        key = (N, bool(use_graph), schedule.key(), explicit, slerp_t, bool(use_mask) if explicit else False,
+               bool(record_dh), bool(record_process))
         with torch.cuda.device(self.device):
-            steps = schedule.steps
-            n_sto = sum(1 for s in steps if s.c1 != 0.0)
+            n_sto = schedule.n_stochastic
             if n_sto:
-                assert noise is not None and noise.shape[0] == n_sto, "pre-drawn noise required for eta>0 steps"
-            g = self.graphs.get(key)
+                assert noise is not None and noise.shape[0] == n_sto, "pre-drawn noise required for stochastic steps"
+            # kernel variants / parameters baked at capture time (all part of `key`)
+            self.state["ignore_timestep"] = schedule.ignore_timestep
+            self.state["slerp_t"], self.state["use_mask"] = slerp_t, bool(use_mask)
+            if record_dh and (explicit or self.n_delta == 0):
+                raise ops._lib.AsyrpError("record_dh needs the DeltaBlock path")
+            g = self.graphs.pop(key, None)
             if g is None:
-                t_table = torch.tensor([[float(s.t)] * N for s in steps], dtype=torch.float32, device=self.device)
-                zbuf = torch.zeros((max(n_sto, 1), *P.x.shape), dtype=torch.float32, device=self.device)
-                P.set_coeffs(schedule.hs_coeff)
-                self.state["ignore_timestep"] = False
-
-                def body():
-                    zi = 0
-                    for k, s in enumerate(steps):
-                        P.t.copy_(t_table[k])
-                        P.run_encoder()
-                        edit = s.edit and self.n_delta > 0
-                        if edit:
-                            P.run_edit()
-                        P.run_decoder()
-                        z = None
-                        if s.c1 != 0.0:
-                            z = zbuf[zi]
-                            zi += 1
-                        ops.ddim_update(P.x, P.et, P.et_mod if edit else P.et, z, P.x, None, s.at, s.an, s.c1, s.c2)
-
-                n_launch = sum(len(P.launches(s.edit and self.n_delta > 0)) + 1 for s in steps)
-                g = {"zbuf": zbuf, "t_table": t_table, "body": body, "graph": None, "launches": n_launch}
-                if use_graph:
-                    P.x.copy_(x_T)
-                    s_ = torch.cuda.Stream(device=self.device)
-                    s_.wait_stream(torch.cuda.current_stream())
-                    with torch.cuda.stream(s_):
-                        # warm-up launch outside capture (lazy function attributes, first-touch)
-                        P.t.copy_(t_table[0])
-                        P.run_encoder()
-                        P.run_edit() if self.n_delta else None
-                        P.run_decoder()
-                    torch.cuda.current_stream().wait_stream(s_)
-                    torch.cuda.synchronize(self.device)
-                    cg = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(cg):
-                        body()
-                    g["graph"] = cg
-                self.graphs[key] = g
+                g = self._build_trajectory(P, schedule, use_graph, explicit, record_dh, record_process)
+                while len(self.graphs) >= self.MAX_GRAPHS:
+                    self.graphs.pop(next(iter(self.graphs)))
+            self.graphs[key] = g  # most recently used last
             self.last_launches = g["launches"]
+            self.last_records = g["rec"]
+            P.set_coeffs(schedule.hs_coeff)
+            if explicit and g["n_edit"]:
+                dh = delta_hs.to(self.device, torch.float32)
+                assert dh.shape[0] == g["n_edit"], f"delta_hs has {dh.shape[0]} rows, schedule has {g['n_edit']} edit steps"
+                g["rec"]["dh_in"].copy_(dh if dh.dim() == 5 else dh[:, None].expand_as(g["rec"]["dh_in"]))
             P.x.copy_(x_T, non_blocking=True)
             if n_sto:
                 g["zbuf"].copy_(noise, non_blocking=True)

@@ -87,7 +87,7 @@ class ConvOp:
 
     def __init__(self, segs, weight, out=None, ebias=None, ebias_stride=0, residual=None, res_scale=1.0,
                  acc_scale=1.0, stats=None, out_planar=None, out_shape=None, weight_batched=False, a_heads=1,
-                 b_heads=1, out_heads=1, up2=False):
+                 b_heads=1, out_heads=1, up2=False, scales=None):
         lib = _lib.load()
         segs = [tuple(sg) + (None, 0, 0) * (len(sg) == 2) for sg in segs]
         srcs = [sg[0] for sg in segs]
@@ -136,13 +136,16 @@ class ConvOp:
         d.ebias_stride = ebias_stride
         d.residual = residual.data_ptr() if residual is not None else None
         d.res_scale, d.acc_scale = res_scale, acc_scale
+        if scales is not None:  # device-side (acc_scale, res_scale): overrides the two values above at run time
+            assert scales.dtype == torch.float32 and scales.is_cuda and scales.numel() >= 2 and scales.is_contiguous()
+            d.scales = scales.data_ptr()
         d.out = out.data_ptr() if out is not None else None
         d.stats = stats.data_ptr() if stats is not None else None
         if out_planar is not None:
             assert out_planar.dtype == torch.float32
             d.out_planar = out_planar.data_ptr()
             d.planar_c = out_planar.shape[1]
-        self._keep = (srcs, affs, weight, out, ebias, residual, stats, out_planar)
+        self._keep = (srcs, affs, weight, out, ebias, residual, stats, out_planar, scales)
         h = C.c_void_p()
         check(lib.asyrp_conv_create(C.byref(d), C.byref(h)), "asyrp_conv_create")
         self._h = h

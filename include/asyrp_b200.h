@@ -27,6 +27,15 @@ extern "C" {
 
 const char* asyrp_last_error(void);
 
+/* Programmatic dependent launch: every kernel of the library begins with griddepcontrol.launch_dependents and
+ * executes griddepcontrol.wait before its first global-memory access, and is launched with the
+ * programmaticStreamSerialization attribute, so consecutive kernels of a stream (or of a captured graph) overlap
+ * launch latency and prologue with the predecessor's tail.  Results are unchanged.  Default on (ASYRP_PDL=0 in the
+ * environment or asyrp_set_pdl(0) turns it off).  The reference's equivalent is the implicit stream order of
+ * PyTorch's eager launches (one or more library kernels per line of models/ddpm/diffusion.py:473-580). */
+int asyrp_set_pdl(int enabled);
+int asyrp_get_pdl(void);
+
 /* ---- implicit-GEMM convolution on tcgen05 tensor cores ------------------------------------------------
  * Replaces torch.nn.Conv2d / Conv1d(k=1) / bmm call sites of the UNets:
  *   ResnetBlock.conv1/conv2/nin_shortcut  models/ddpm/diffusion.py:122-149     (3x3 s1 p1, 1x1)
@@ -89,6 +98,10 @@ typedef struct AsyrpConvDesc {
    * weight is fp16 [4*Cout][4*C] (phase-major rows, 2x2 taps x C; the 3x3 taps that fall on one source pixel are
    * pre-summed), stats has asyrp_conv_stats_tiles_up2() slots.  4/9 of the MACs, no upsampled tensor. */
   int up2;
+  /* optional DEVICE pointer to two floats (acc_scale, res_scale) read by the kernel at run time instead of the
+   * by-value fields: the DeltaBlock coefficients hs_coeff are per-call arguments of forward()
+   * (ddpm/diffusion.py:512-516), so one captured trajectory graph serves every coefficient tuple */
+  const float* scales;
 } AsyrpConvDesc;
 
 /* number of tile slots of the stats buffer of a conv with this output geometry; has_3x3: the conv has an

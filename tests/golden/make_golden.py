@@ -1,7 +1,7 @@
 """Generate the golden fixtures under tests/golden/ by running the REFERENCE'S OWN modules (imported from
 /root/reference, which only exists in the build container) on the synthetic weights of oracle/synth.py.
 
-    python tests/golden/make_golden.py [--full]
+    python tests/golden/make_golden.py [--full] [--traj celeba16,afhq,imagenet]
 
 The fixtures pin the oracle (tests/test_oracle.py, CPU) and are what the CUDA engine is compared with on the GPU
 box, where /root/reference does not exist.  Nothing here is imported by the product package.
@@ -12,6 +12,12 @@ Fixtures (npz, fp32):
   ddpm_celeba_fwd.npz               CelebA-HQ config, 256x256, B=1, Asyrp forward at t=999 (stride-4 subsample)
   ddpm_celeba_traj40.npz            40-step Asyrp edit trajectory, B=1 (stride-4 subsample of x_0 + per-step |x0_t| max)
   adm_afhq_fwd.npz, adm_imagenet_fwd.npz   one Asyrp forward each (stride-4 subsample)
+  checkpoint/*.pth                  the three shipped DeltaBlocks SURVEY §8(d) names, key "0" only
+                                    ({"0": layer_0.state_dict()}, the part diffusion_latent.py:674-676 loads)
+  ddpm_celeba_smiling_traj40_b16.npz   BASELINE configs[1] in full: B=16, 40-step edit, 'smiling' DeltaBlock
+  adm_afhq_happy_traj40.npz            configs[2] at B=1: iDDPM-AFHQ, 'dog_happy' DeltaBlock, 40 steps
+  adm_imagenet_traj50.npz              configs[4] at B=1: ADM-ImageNet, seeded DeltaBlock, 50 steps
+                                    (trajectory fixtures: stride-4 subsample of x_0, |x_0| max, seeds, sequence)
 """
 import argparse
 import os
@@ -215,11 +221,86 @@ def full_trajectory(model, sd, cfg):
     print(f"ddpm_celeba_traj40 ok ({time.time() - t0:.1f}s): |x_0|max={xf.abs().max():.2f}")
 
 
+SHIPPED = {"celeba": "smiling_LC_CelebA_HQ_t999_ninv40_ngen40_0.pth", "afhq": "dog_happy_LC_dog_t999_ninv40_ngen40_0.pth",
+           "church": "church_gothic_LC_church_outdoor_t999_ninv40_ngen40_0.pth"}
+
+
+def shipped_delta_block(key):
+    """copy the DeltaBlock weights of a shipped checkpoint (checkpoint/<name>.pth, key "0") into tests/golden/checkpoint/"""
+    src = torch.load(os.path.join(REF, "checkpoint", SHIPPED[key]), map_location="cpu", weights_only=True)
+    os.makedirs(os.path.join(HERE, "checkpoint"), exist_ok=True)
+    blk = {k: v.clone() for k, v in src["0"].items()}
+    torch.save({"0": blk}, os.path.join(HERE, "checkpoint", SHIPPED[key]))
+    return blk
+
+
+@torch.no_grad()
+def trajectory_fixture(name, family, cfg, key, B, n_step, chunk=4):
+    """BASELINE workload `name`: the reference's own modules + denoising_step, synthetic seeded UNet weights
+    (torch_default style), the shipped DeltaBlock where one exists, x_T = randn(B,3,256,256; seed 1234), pre-drawn noise
+    (seed 4321, one draw per sequence entry in ascending order), t_edit=500, t_addnoise=200, hs_coeff (1,1)"""
+    t0 = time.time()
+    if family == "ddpm":
+        shapes = o_ddpm.ddpm_param_shapes(cfg, 1)
+        model = ref_ddpm(cfg, 1)
+        fwd = lambda sd, *a, **k: o_ddpm.ddpm_forward(sd, cfg, *a, **k)  # noqa: E731
+    else:
+        shapes = o_adm.adm_param_shapes(cfg, 1)
+        model = ref_adm(cfg, 1)
+        fwd = lambda sd, *a, **k: o_adm.adm_forward(sd, cfg, *a, **k)  # noqa: E731
+    sd = synth.synth_state_dict(shapes, seed=1234, style="torch_default")
+    if key in SHIPPED:
+        for k, v in shipped_delta_block(key).items():
+            assert sd["layer_0." + k].shape == v.shape, k
+            sd["layer_0." + k] = v
+    load_checked(model, shapes, sd)
+    g = torch.Generator().manual_seed(1234)
+    x = torch.randn(B, 3, 256, 256, generator=g)
+    betas = o_smp.make_betas()
+    seq, seq_next = o_smp.make_sequences(999, n_step)
+    gn = torch.Generator().manual_seed(4321)
+    noises = {i: torch.randn(x.shape, generator=gn) for i in seq}
+    outs = []
+    for c0 in range(0, B, chunk):
+        sl = slice(c0, min(B, c0 + chunk))
+        nz = {i: v[sl] for i, v in noises.items()}
+        rec = []
+        xf = ref_trajectory(model, x[sl], betas, seq, seq_next, 500, 200, family == "adm", nz, rec)
+        if c0 == 0:  # the oracle restatement must reproduce the reference bit for bit (first sample)
+            xo = o_smp.run_trajectory(lambda *a, **k: fwd(sd, *a, **k), x[:1], betas=betas, seq=seq, seq_next=seq_next,
+                                      t_edit=500, t_addnoise=200, index=0, hs_coeff=(1.0, 1.0),
+                                      learn_sigma=family == "adm", noises={i: v[:1] for i, v in noises.items()})
+            assert torch.equal(xo, xf[:1]), (xo - xf[:1]).abs().max()
+        outs.append(xf)
+        print(f"  {name}: samples {sl.start}..{sl.stop - 1} done ({time.time() - t0:.0f}s)", flush=True)
+    xf = torch.cat(outs)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), x0_sub=sub(xf), x0_absmax=np.array(xf.abs().max().item()),
+                        x0_absmax_per_sample=xf.abs().amax(dim=(1, 2, 3)).numpy(), x0_std=np.array(xf.double().std().item()),
+                        batch=np.array(B), x_seed=np.array(1234), noise_seed=np.array(4321), seq=np.array(seq),
+                        t_edit=np.array(500), t_addnoise=np.array(200))
+    print(f"{name} ok ({time.time() - t0:.1f}s): |x_0|max={xf.abs().max():.2f}")
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--full", action="store_true", help="also the 256x256 fixtures (minutes of CPU time)")
+    ap.add_argument("--traj", default="", help="comma list of trajectory fixtures: celeba16, afhq, imagenet, church")
+    ap.add_argument("--skip-mini", action="store_true")
     args = ap.parse_args()
     torch.set_num_threads(os.cpu_count())
+    for t in [t for t in args.traj.split(",") if t]:
+        if t == "celeba16":
+            trajectory_fixture("ddpm_celeba_smiling_traj40_b16", "ddpm", o_ddpm.CELEBA_CFG, "celeba", 16, 40)
+        elif t == "afhq":
+            trajectory_fixture("adm_afhq_happy_traj40", "adm", o_adm.AFHQ_HP, "afhq", 1, 40)
+        elif t == "imagenet":
+            trajectory_fixture("adm_imagenet_traj50", "adm", o_adm.IMAGENET_HP, "imagenet", 1, 50)
+        elif t == "church":
+            shipped_delta_block("church")
+        else:
+            raise SystemExit(f"unknown trajectory fixture {t}")
+    if args.skip_mini:
+        sys.exit(0)
     mini("ddpm")
     mini("adm")
     if args.full:

@@ -212,3 +212,96 @@ def test_upconv_subpixel_weights():
     assert (out - ref).abs().max() < 2e-2 * ref.abs().max()  # fp16 rounding of the packed weights
     pk32 = ops.pack_upconv_weight(wt.float())
     assert pk32.shape == (4 * co, 4 * ci) and pk32.dtype == torch.float16
+
+
+@pytest.mark.parametrize("mode", ["ddpm", "dt_lambda", "ignore"])
+def test_schedule_sample_type_dt_lambda_and_key(mode):
+    """Schedule carries what save_image forwards to denoising_step on every step (diffusion_latent.py:507-520):
+    'ddpm' ancestral coefficients, the dt_lambda override at t >= 999, ignore_timestep; the coefficients reproduce the
+    oracle's step; hs_coeff VALUES are not part of the graph key (they are device-side parameters)"""
+    from asyrp_official_b200.schedule import Schedule, make_sequences
+    from oracle import sampler as osmp
+    betas = osmp.make_betas()
+    logvar = osmp.make_logvar(osmp.get_beta_schedule(beta_start=1e-4, beta_end=0.02, num_diffusion_timesteps=1000))
+    seq, nxt = make_sequences(999, 10)
+    base = Schedule(betas, seq, nxt, t_edit=500, t_addnoise=0, hs_coeff=(1.0, 1.0))
+    assert base.key() == Schedule(betas, seq, nxt, t_edit=500, t_addnoise=0, hs_coeff=(0.3, 2.0)).key()
+    g = torch.Generator().manual_seed(0)
+    x, e, z = (torch.randn(1, 3, 4, 4, generator=g) for _ in range(3))
+    model = lambda xt, t, **k: (e, e, None, None)  # noqa: E731
+    if mode == "ignore":
+        s2 = Schedule(betas, seq, nxt, t_edit=500, t_addnoise=0, hs_coeff=(1.0, 1.0), ignore_timestep=True)
+        assert s2.key() != base.key() and s2.ignore_timestep
+        return
+    if mode == "ddpm":
+        sch = Schedule(betas, seq, nxt, t_edit=500, t_addnoise=0, hs_coeff=(1.0, 1.0), sample_type="ddpm", logvars=logvar)
+        assert sch.n_stochastic == 10 and sch.key() != base.key() and sch.steps[-1].mask == 0.0
+        for s in (sch.steps[0], sch.steps[-1]):
+            ref = osmp.denoising_step(x, torch.ones(1) * s.t, torch.ones(1) * s.t_next, model=model, b=betas,
+                                      logvars=logvar, sampling_type="ddpm", noise=z)[0]
+            at, bt = torch.tensor(s.at), torch.tensor(s.bt)
+            mine = 1 / torch.sqrt(1.0 - bt) * (x - bt / torch.sqrt(1 - at) * e) + s.mask * torch.exp(
+                torch.tensor(0.5 * s.logvar)) * z
+            assert torch.allclose(ref, mine, rtol=0, atol=1e-6)
+        with pytest.raises(ValueError):
+            Schedule(betas, seq, nxt, t_edit=500, sample_type="ddpm", dt_lambda=0.5, logvars=logvar)
+        return
+    sch = Schedule(betas, seq, nxt, t_edit=500, t_addnoise=0, hs_coeff=(1.0, 1.0), dt_lambda=0.7)
+    assert sch.key() != base.key() and sch.steps[1] == base.steps[1]  # only t >= dt_end = 999 is affected
+    s = sch.steps[0]
+    ref = osmp.denoising_step(x, torch.ones(1) * s.t, torch.ones(1) * s.t_next, model=model, b=betas, dt_lambda=0.7)[0]
+    at, an = torch.tensor(s.at), torch.tensor(s.an)
+    mine = an.sqrt() * ((x - e * (1 - at).sqrt()) / at.sqrt()) + torch.tensor(s.c2) * e
+    assert torch.allclose(ref, mine, rtol=0, atol=1e-6) and s.c1 == 0.0
+
+
+def test_reference_staging_script(tmp_path):
+    """scripts/stage_reference.py copies the reference's hot-path sources verbatim into a git-ignored directory
+    (only where /root/reference exists, i.e. in the build container)"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("stage_reference", os.path.join(ROOT, "scripts", "stage_reference.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert "baseline/_ref/" in open(os.path.join(ROOT, ".gitignore")).read()
+    if not os.path.isdir("/root/reference"):
+        assert mod.stage("/root/reference", str(tmp_path / "x"), quiet=True) is False
+        return
+    assert mod.stage("/root/reference", str(tmp_path / "ref"), quiet=True)
+    for rel in ("utils/diffusion_utils.py", "models/ddpm/diffusion.py", "models/improved_ddpm/unet.py",
+                "models/guided_diffusion/unet.py", "configs/celeba.yml",
+                "checkpoint/smiling_LC_CelebA_HQ_t999_ninv40_ngen40_0.pth"):
+        a, b = os.path.join("/root/reference", rel), os.path.join(str(tmp_path / "ref"), rel)
+        assert open(a, "rb").read() == open(b, "rb").read(), rel
+
+
+def test_engine_numerics_emulation_switches():
+    """oracle/emulate.py with every rounding switched off is the fp32 oracle; switched on it differs at the fp16 level"""
+    from oracle import ddpm as od, emulate as em, synth
+    cfg = od.MINI_CFG
+    sd = synth.synth_state_dict(od.ddpm_param_shapes(cfg, 1), 1234, "jittered")
+    x, t = synth.synth_noise((1, 3, 32, 32), 1234), torch.ones(1) * 700
+    ref = od.ddpm_forward(sd, cfg, x, t, index=0, t_edit=500, hs_coeff=(1.0, 0.7))
+    off = em.ddpm_forward(sd, cfg, x, t, index=0, t_edit=500, hs_coeff=(1.0, 0.7), flags=em.NONE)
+    on = em.ddpm_forward(sd, cfg, x, t, index=0, t_edit=500, hs_coeff=(1.0, 0.7), flags=em.ALL)
+    for a, b, c in zip(ref, off, on):
+        scale = a.abs().max().item()
+        assert (a - b).abs().max().item() <= 2e-5 * scale
+        assert 1e-5 * scale < (a - c).abs().max().item() < 1e-2 * scale
+
+
+def test_shipped_delta_block_fixtures_load():
+    """tests/golden/checkpoint/*.pth: the DeltaBlocks SURVEY §8(d) names, in the {"0": state_dict} format run_test loads"""
+    from asyrp_official_b200 import modules
+    from asyrp_official_b200.configs import load_config
+    d = os.path.join(ROOT, "tests", "golden", "checkpoint")
+    m = modules.DDPM(load_config("celeba"))
+    m.setattr_layers(1)
+    for name in ("smiling_LC_CelebA_HQ_t999_ninv40_ngen40_0.pth", "church_gothic_LC_church_outdoor_t999_ninv40_ngen40_0.pth"):
+        ck = torch.load(os.path.join(d, name), map_location="cpu", weights_only=True)
+        res = m.layer_0.load_state_dict(ck["0"])
+        assert not res.missing_keys and not res.unexpected_keys
+    a = modules.i_DDPM("AFHQ")
+    a.setattr_layers(1)
+    ck = torch.load(os.path.join(d, "dog_happy_LC_dog_t999_ninv40_ngen40_0.pth"), map_location="cpu", weights_only=True)
+    res = a.layer_0.load_state_dict(ck["0"])
+    assert not res.missing_keys and not res.unexpected_keys
