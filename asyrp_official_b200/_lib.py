@@ -37,6 +37,7 @@ class AsyrpConvDesc(C.Structure):
         ("planar_c", c_int),
         ("up2", c_int),
         ("scales", c_void_p),
+        ("res_mode", c_int),
     ]
 
 
@@ -47,6 +48,8 @@ SIGNATURES = {
     "asyrp_get_pdl": (c_int, []),
     "asyrp_conv_stats_tiles": (c_int, [c_int, c_int, c_int, c_int]),
     "asyrp_conv_stats_tiles_up2": (c_int, [c_int, c_int, c_int]),
+    "asyrp_set_cta2": (c_int, [c_int]),
+    "asyrp_conv_is_cta2": (c_int, [c_void_p]),
     "asyrp_conv_create": (c_int, [C.POINTER(AsyrpConvDesc), C.POINTER(c_void_p)]),
     "asyrp_conv_launch": (c_int, [c_void_p, c_void_p]),
     "asyrp_conv_set_scales": (c_int, [c_void_p, c_float, c_float]),

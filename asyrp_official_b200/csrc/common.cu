@@ -77,7 +77,7 @@ static int g_pdl = -1;
 int pdl_enabled() {
   if (g_pdl < 0) {
     const char* e = getenv("ASYRP_PDL");
-    g_pdl = (e != nullptr && e[0] == '0') ? 0 : 1;
+    g_pdl = (e != nullptr && e[0] == '1') ? 1 : 0;
   }
   return g_pdl;
 }

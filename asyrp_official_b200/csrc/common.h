@@ -61,9 +61,11 @@ int sm_count();
 // Programmatic dependent launch (PDL).  Every kernel of the library starts with `griddepcontrol.launch_dependents`
 // and executes `griddepcontrol.wait` before its first global-memory access; launched with the
 // programmaticStreamSerialization attribute, kernel i+1 is scheduled (and runs its prologue: barrier init, TMEM
-// allocation, descriptor prefetch) while kernel i drains, instead of after it — inside a captured graph too.  The
-// ~300 launches of one UNet evaluation otherwise each pay the full launch gap.  asyrp_set_pdl(0) / ASYRP_PDL=0
-// restores plain stream-ordered launches.
+// allocation, descriptor prefetch) while kernel i drains, instead of after it — inside a captured graph too.
+// Measured on the 40-step trajectory graph (round 2, B200): 443.0 ms without vs 448.7 ms with PDL — inside a CUDA graph
+// the launch gaps are already hidden and a 227 KB / 608-thread CTA cannot become resident before its predecessor on
+// the same SM has exited, so there is nothing to overlap.  Hence OFF by default; asyrp_set_pdl(1) / ASYRP_PDL=1
+// enables it (eager, launch-bound callers of the C ABI benefit).
 int pdl_enabled();
 
 template <typename... Exp, typename... Act>

@@ -73,6 +73,9 @@ struct ConvParams {
   const float* ebias;      // fp32 bias (+ timestep-embedding projection): row n at ebias + n*ebias_stride
   int ebias_stride;        // 0: one row shared by all samples
   const __half* res;       // residual, NHWC like out, or nullptr
+  // res_mode 1: the residual is nearest-x2 upsampled on the fly (source [N][H/2][W/2][Cout]); 2: 2x2 average-pooled
+  // (source [N][2H][2W][Cout]) — the skip branch of the ADM up / down ResBlocks (improved_ddpm/unet.py:279-284,297)
+  int res_mode;
   float res_scale, acc_scale;
   // optional device-side copy of (acc_scale, res_scale): when set it overrides the two by-value fields, so that one
   // captured CUDA graph serves every hs_coeff tuple (the DeltaBlock coefficients are per-call arguments of forward())
@@ -197,7 +200,7 @@ __device__ __forceinline__ void transform_fast(uint32_t base, uint32_t vld, uint
 template <int TWS, int MT>
 __device__ __forceinline__ void swap_epilogue(const ConvParams& p, uint32_t taddr, int half, size_t obase,
                                               int row_stride, int cout, int lane_off, uint32_t sel, float eb,
-                                              float scale, float rs, float& s1, float& s2) {
+                                              float scale, float rs, size_t rbase, int rrow, float& s1, float& s2) {
   // obase: element offset of the tile's first pixel at this lane's channel; row_stride / cout: elements between
   // vertically / horizontally adjacent tile pixels in the output (doubled for the sub-pixel phases of an up2 conv)
   constexpr int TW = 1 << TWS;
@@ -212,11 +215,36 @@ __device__ __forceinline__ void swap_epilogue(const ConvParams& p, uint32_t tadd
     const size_t o0 = obase + static_cast<size_t>(cc * kRows) * row_stride;
     __half2 rv[16];
     if (resp != nullptr) {  // all residual loads first: independent of the stores below
-      const __half* rp = resp + o0;
+      if (p.res_mode == 0) {
+        const __half* rp = resp + o0;
 #pragma unroll
-      for (int i = 0; i < 32; i += 2)
-        rv[i >> 1] = __halves2half2(rp[(i >> TWS) * row_stride + (i & (TW - 1)) * cout],
-                                    rp[((i + 1) >> TWS) * row_stride + ((i + 1) & (TW - 1)) * cout]);
+        for (int i = 0; i < 32; i += 2)
+          rv[i >> 1] = __halves2half2(rp[(i >> TWS) * row_stride + (i & (TW - 1)) * cout],
+                                      rp[((i + 1) >> TWS) * row_stride + ((i + 1) & (TW - 1)) * cout]);
+      } else if (p.res_mode == 1) {
+        // nearest-x2: tile pixel (dy, dx) reads source pixel (dy >> 1, dx >> 1) of the half-resolution tensor
+        // (tile origins are even); rrow = elements per source row, cout here = p.Cout (no up2 output scatter)
+        const __half* rp = resp + rbase + static_cast<size_t>((cc * kRows) >> 1) * rrow;
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const __half v0 = rp[((i >> TWS) >> 1) * rrow + ((i & (TW - 1)) >> 1) * cout];
+          rv[i >> 1] = __halves2half2(v0, v0);  // pixels i, i+1 share their source pixel (i even)
+        }
+      } else {
+        // 2x2 average pool of the double-resolution tensor, fp32 like F.avg_pool2d
+        const __half* rp = resp + rbase + static_cast<size_t>(cc * kRows * 2) * rrow;
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float a2[2];
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const __half* q = rp + ((i + k) >> TWS) * 2 * rrow + ((i + k) & (TW - 1)) * 2 * cout;
+            a2[k] = 0.25f * ((__half2float(q[0]) + __half2float(q[cout])) +
+                             (__half2float(q[rrow]) + __half2float(q[rrow + cout])));
+          }
+          rv[i >> 1] = __floats2half2_rn(a2[0], a2[1]);
+        }
+      }
     }
     tmem_ld_wait();
     float v[32];
@@ -254,7 +282,16 @@ __device__ __forceinline__ void swap_epilogue(const ConvParams& p, uint32_t tadd
 // N side of ONE N=256 MMA per K step, so D is [channel lane][pixel column].  Per MMA the tensor core then reads
 // 4 KB (weights) + 8 KB (pixels) of shared memory per 128 cycles instead of 4 + 4 KB per 64 cycles: the Cout=128
 // layers (70% of the FLOPs) stop being shared-memory-bandwidth bound.
-template <int BN, int MT, bool SWAP = false>
+//
+// CTA2: the kernel runs as clusters of two CTAs (one TPC) that share every weight tile.  Each CTA keeps its own
+// 128-pixel tile (A operand, loaded and transformed locally) and HALF of the 256 weight rows (B operand) in its shared
+// memory; the leader (cluster rank 0) issues `tcgen05.mma.cta_group::2` with M = 256: per K step each SM reads
+// 4 + 4 KB of operands instead of 4 + 8 KB and ingests 16 instead of 32 KB of weights per stage (the 128 px x 256 ch
+// tile of one CTA is bound by exactly that ingest, 64 of the ~66 B/clk one SM takes).  Synchronisation: TMA bytes of
+// both weight halves are counted on the leader's fullB barrier; transform warps of both CTAs arrive on the leader's
+// readyA; MMA completion is committed to both CTAs' empty / tmem-full barriers (multicast); both epilogues arrive on
+// the leader's tmem-empty barrier.  Numerically identical to the one-CTA kernel (same K order per tile).
+template <int BN, int MT, bool SWAP = false, bool CTA2 = false>
 __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvParams p) {
   pdl_trigger();  // the next kernel of the stream may be scheduled as soon as every CTA of this grid is running
   extern __shared__ uint8_t smem_raw[];
@@ -263,8 +300,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
 
   const int warp = uniform_warp_id();
   const int lane = threadIdx.x & 31;
-  constexpr uint32_t kBStage = BN * 128;
+  constexpr uint32_t kBStage = (CTA2 ? BN / 2 : BN) * 128;
   static_assert(!SWAP || (BN == 128 && MT == 2), "swapped-operand variant: 128 channels x 256 pixels");
+  static_assert(!CTA2 || (BN == 256 && MT == 1 && !SWAP), "CTA-pair variant: 2 x 128 pixels x 256 channels");
+  const uint32_t cta_rank = CTA2 ? cluster_ctarank() : 0u;
   constexpr uint32_t kAccCols = SWAP ? MT * 128 : MT * BN;  // fp32 columns of one accumulator set
   constexpr uint32_t kTmemCols = 2 * kAccCols;                // two sets (epilogue / MMA overlap)
   static_assert(kTmemCols <= 512 && kTmemCols >= 32, "TMEM budget");
@@ -289,7 +328,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
     for (int i = 0; i < n_aslots; ++i) {
       mbar_init(&fullA[i], 1);
       mbar_init(&emptyA[i], 1);
-      mbar_init(&readyA[i], kNumTransformWarps);
+      mbar_init(&readyA[i], (CTA2 ? 2 : 1) * kNumTransformWarps);
     }
     for (int i = 0; i < p.b_stages; ++i) {
       mbar_init(&fullB[i], 1);
@@ -297,7 +336,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], kNumEpilogueWarps);
+      mbar_init(&tempty[i], (CTA2 ? 2 : 1) * kNumEpilogueWarps);
     }
     fence_mbar_init();
   }
@@ -306,11 +345,17 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
     tma_prefetch_desc(&p.tmB);
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, kTmemCols);
-    tmem_relinquish();
+    if constexpr (CTA2) {
+      tmem_alloc_2cta(tmem_slot, kTmemCols);
+      tmem_relinquish_2cta();
+    } else {
+      tmem_alloc(tmem_slot, kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CTA2) cluster_sync_all();  // the peer's barriers are initialised before anything arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the previous kernel's tail; from
@@ -318,6 +363,17 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
   pdl_wait();
 
   const int total_tiles = p.m_tiles * p.n_tiles;
+  // work items: output tiles, or (CTA2) pairs of horizontally adjacent pixel tiles sharing one weight tile; a CTA of a
+  // pair processes tile 2*pm + rank of channel tile nt
+  const int n_workers = CTA2 ? gridDim.x / 2 : gridDim.x;
+  const int worker0 = CTA2 ? blockIdx.x / 2 : blockIdx.x;
+  const int n_work = CTA2 ? total_tiles / 2 : total_tiles;
+  auto own_tile = [&](int w) -> int {
+    if constexpr (!CTA2) return w;
+    const int half_m = p.m_tiles >> 1;
+    const int nt_ = w / half_m;
+    return nt_ * p.m_tiles + 2 * (w - nt_ * half_m) + static_cast<int>(cta_rank);
+  };
 
   if (warp == 0) {
     // ======================================================== TMA producer, A operand (activations)
@@ -327,7 +383,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
     {
       int sa = 0, sl = 0;      // heavy / light ring cursors
       uint32_t pa = 0, pl = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int w = worker0; w < n_work; w += n_workers) {
+        const int tile = own_tile(w);
         const TileCoord tc = tile_coord(p, tile);
         const int x0 = tc.tx * p.TW, y0 = tc.ty * THT, n0 = tc.tn * p.NB;
         for (int e = 0; e < p.n_sched; ++e) {
@@ -372,7 +429,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
     {
       int sb = 0;
       uint32_t pb = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int w = worker0; w < n_work; w += n_workers) {
+        const int tile = own_tile(w);
         const TileCoord tc = tile_coord(p, tile);
         const int nt = tc.nt, tn = tc.tn;
         const int bz = p.b_batched ? tn * p.NB : 0;
@@ -389,7 +447,15 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
                 // nt*BN already select the phase)
                 const int tap = sg.mode == 0 ? 0 : (sg.mode == 1 ? tp * 3 + cp : (sg.mode == 3 ? tp : cp));
                 mbar_wait_suspend(&emptyB[sb], pb ^ 1);
-                if (elect_one()) {
+                if constexpr (CTA2) {
+                  // this CTA's half of the weight rows; the bytes of both halves are counted on the leader's barrier
+                  const uint32_t bar = mapa_shared(smem_u32(&fullB[sb]), 0u);
+                  if (elect_one()) {
+                    if (cta_rank == 0) mbar_arrive_expect_tx(&fullB[sb], 2 * kBStage);
+                    tma_load_4d_2cta(sB + sb * kBStage, &p.tmB, bar, sg.kbase + tap * sg.C + ch * 64,
+                                     nt * BN + static_cast<int>(cta_rank) * (BN / 2), b_h, b_n);
+                  }
+                } else if (elect_one()) {
                   mbar_arrive_expect_tx(&fullB[sb], kBStage);
                   tma_load_4d(sB + sb * kBStage, &p.tmB, &fullB[sb], sg.kbase + tap * sg.C + ch * 64, nt * BN, b_h,
                               b_n);
@@ -403,13 +469,14 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
     }
   } else if (warp == 1) {
     // ======================================================== MMA issuer (whole warp, elected lane issues)
-    {
-      constexpr uint32_t idesc = umma_idesc_f16_m128(SWAP ? MT * 128 : BN);
+    if (!CTA2 || cta_rank == 0) {  // CTA pair: the leader issues for both SMs
+      constexpr uint32_t idesc = CTA2 ? umma_idesc_f16_m256(BN) : umma_idesc_f16_m128(SWAP ? MT * 128 : BN);
       const uint32_t b_lo0 = umma_desc_lo(smem_u32(sB));
       int sa = 0, sl = 0, sb = 0;
       uint32_t pa = 0, pl = 0, pb = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      for (int w = worker0; w < n_work; w += n_workers, ++it) {
+        const int tile = own_tile(w);
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait_suspend(&tempty[acc], acc_phase ^ 1);
@@ -445,7 +512,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
           {
             for (int cp = 0; cp < ncopies; ++cp) {
               const int slot = lt ? p.a_stages + sl : sa;
-              mbar_wait(p.any_transform ? &readyA[slot] : &fullA[slot], lt ? pl : pa);
+              mbar_wait((p.any_transform || CTA2) ? &readyA[slot] : &fullA[slot], lt ? pl : pa);
               tc_fence_after();
               uint32_t a_lo =
                   umma_desc_lo(smem_u32(lt ? sL + sl * p.l_stage_bytes : sA + sa * p.a_stage_bytes)) + first16;
@@ -455,7 +522,11 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
                 tc_fence_after();
                 const uint32_t b_lo = b_lo0 + sb * (kBStage >> 4);
                 if (elect_one()) {
-                  if constexpr (SWAP) {
+                  if constexpr (CTA2) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                      umma_f16_w_2cta(d_tmem, a_lo + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc, (accumulate | k) ? 1u : 0u);
+                  } else if constexpr (SWAP) {
                     // M = 128 weight rows, N = all MT*128 pixel rows (uniform 8-row-group pitch across sub-tiles)
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
@@ -469,13 +540,15 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
                                    (accumulate | k) ? 1u : 0u);
                     }
                   }
-                  umma_commit(&emptyB[sb]);
+                  if constexpr (CTA2) umma_commit_2cta(&emptyB[sb]); else umma_commit(&emptyB[sb]);
                 }
                 accumulate = 1;
                 if (++sb == p.b_stages) { sb = 0; pb ^= 1; }
                 if (++kx == kxn) { kx = 0; a_lo += wrap16; } else { a_lo += step16; }
               }
-              if (elect_one()) umma_commit(&emptyA[slot]);
+              if (elect_one()) {
+                if constexpr (CTA2) umma_commit_2cta(&emptyA[slot]); else umma_commit(&emptyA[slot]);
+              }
               if (lt) {
                 if (++sl == p.l_stages) { sl = 0; pl ^= 1; }
               } else {
@@ -484,13 +557,15 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
             }
           }
         }
-        if (elect_one()) umma_commit(&tfull[acc]);
+        if (elect_one()) {
+          if constexpr (CTA2) umma_commit_2cta(&tfull[acc]); else umma_commit(&tfull[acc]);
+        }
       }
     }
     __syncwarp();
   } else if (warp >= kWarpT) {
     // ======================================================== operand transform warps, in place
-    if (p.any_transform) {
+    if (p.any_transform || CTA2) {  // CTA pair: these warps also relay "A stage landed" to the leader's barrier
       constexpr int kLanes = kNumTransformWarps * 4;  // pixels handled concurrently (8 threads per pixel)
       const int tt = threadIdx.x - kWarpT * 32;
       const int jl = tt & 7;                  // logical 16B chunk = channels [jl*8, jl*8+8) of the 64-channel slab
@@ -516,7 +591,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
       }
       int sa = 0, sl = 0;
       uint32_t pa = 0, plt = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int w = worker0; w < n_work; w += n_workers) {
+        const int tile = own_tile(w);
         const TileCoord tc = tile_coord(p, tile);
         const int x0 = tc.tx * p.TW, y0 = tc.ty * THT, n0 = tc.tn * p.NB;
         for (int e = 0; e < p.n_sched; ++e) {
@@ -623,7 +699,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
                 fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
               }
               __syncwarp();
-              if (lane == 0) mbar_arrive(&readyA[slot]);
+              if (lane == 0) {
+                if constexpr (CTA2) mbar_arrive_remote(mapa_shared(smem_u32(&readyA[slot]), 0u));
+                else mbar_arrive(&readyA[slot]);
+              }
               if (lt) {
                 if (++sl == p.l_stages) { sl = 0; plt ^= 1; }
               } else {
@@ -650,7 +729,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
       res_scale = __ldg(p.scales + 1);
     }
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int w = worker0; w < n_work; w += n_workers, ++it) {
+      const int tile = own_tile(w);
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const TileCoord tc = tile_coord(p, tile);
@@ -688,13 +768,20 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
         const int pix_stride = p.Cout * ps, row_stride = OW * pix_stride;
         const int lane_off = odd ? pix_stride - 1 : 0;
         const size_t obase = ((static_cast<size_t>(tn) * OH + ty * THT * ps + pa) * OW + tx * p.TW * ps + pb) * p.Cout + c;
+        // residual source geometry for res_mode 1 (half resolution) / 2 (double resolution)
+        const int rW = p.res_mode == 1 ? (p.W >> 1) : (p.W << 1), rH = p.res_mode == 1 ? (p.H >> 1) : (p.H << 1);
+        const int rrow = rW * p.Cout;
+        const size_t rbase =
+            p.res_mode == 1
+                ? ((static_cast<size_t>(tn) * rH + ((ty * THT) >> 1)) * rW + ((tx * p.TW) >> 1)) * p.Cout + c
+                : ((static_cast<size_t>(tn) * rH + ty * THT * 2) * rW + tx * p.TW * 2) * p.Cout + c;
         float s1 = 0.f, s2 = 0.f;
         if (p.TW == 8)
           swap_epilogue<3, MT>(p, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kAccCols, half, obase,
-                               row_stride, pix_stride, lane_off, sel, eb, acc_scale, res_scale, s1, s2);
+                               row_stride, pix_stride, lane_off, sel, eb, acc_scale, res_scale, rbase, rrow, s1, s2);
         else
           swap_epilogue<4, MT>(p, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kAccCols, half, obase,
-                               row_stride, pix_stride, lane_off, sel, eb, acc_scale, res_scale, s1, s2);
+                               row_stride, pix_stride, lane_off, sel, eb, acc_scale, res_scale, rbase, rrow, s1, s2);
         if (p.stats != nullptr) {
           // channel pair = lanes (2j, 2j+1); each (tile, half) owns one slot: nothing to reduce across warps
           s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
@@ -703,6 +790,27 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
             *reinterpret_cast<float2*>(p.stats + ((static_cast<size_t>(tn) * tiles_per_sample * 2 +
                                                     tile_in_sample * 2 + half) * (p.Cout / 2) + (c >> 1)) * 2) =
                 make_float2(s1, s2);
+        }
+      } else if constexpr (BN == 16) {
+        // narrow-N tile of conv_out (3 / 6 real output channels, fp32 planar store): one 16-column load per sub-tile,
+        // warps of the second half have nothing to drain
+        if (half == 0) {
+#pragma unroll 1
+          for (int sub = 0; sub < MT; ++sub) {
+            const int y = ty * THT + sub * p.TH + yy;
+            const bool valid = (x < p.W) && (y < p.H) && (n < p.N);
+            uint32_t r[16];
+            tmem_ld_32x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * (MT * BN) + sub * BN, r);
+            tmem_ld_wait();
+            if (valid) {
+              const float* eb = p.ebias != nullptr ? p.ebias + static_cast<size_t>(n) * p.ebias_stride : nullptr;
+              const size_t hw = static_cast<size_t>(p.H) * p.W;
+              float* pp = p.out_planar + static_cast<size_t>(n) * p.planar_c * hw + static_cast<size_t>(y) * p.W + x;
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                if (i < p.planar_c) pp[i * hw] = (__uint_as_float(r[i]) + (eb != nullptr ? eb[i] : 0.f)) * acc_scale;
+            }
+          }
         }
       } else {
 #pragma unroll 1
@@ -737,16 +845,43 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
             for (int i = 0; i < 32; ++i) v[i] *= acc_scale;
           }
           if (p.res != nullptr && valid) {
-            const uint4* rp = reinterpret_cast<const uint4*>(p.res + pix + c0);
+            if (p.res_mode == 2) {
+              // skip branch of a down ResBlock: 2x2 average of the double-resolution tensor, fp32
+              const size_t rW = static_cast<size_t>(p.W) * 2;
+              const __half* r0 = p.res + ((static_cast<size_t>(n) * p.H * 2 + y * 2) * rW + x * 2) * p.Cout + c0;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint4 u = rp[j];
-              const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+              for (int j = 0; j < 4; ++j) {
+                float a8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const float2 f = __half22float2(h2[k]);
-                v[j * 8 + k * 2] += res_scale * f.x;
-                v[j * 8 + k * 2 + 1] += res_scale * f.y;
+                for (int q4 = 0; q4 < 4; ++q4) {
+                  const uint4 u = *reinterpret_cast<const uint4*>(r0 + ((q4 >> 1) * rW + (q4 & 1)) * p.Cout + j * 8);
+                  const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {
+                    const float2 f = __half22float2(h2[k]);
+                    a8[2 * k] += f.x;
+                    a8[2 * k + 1] += f.y;
+                  }
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[j * 8 + k] += res_scale * (0.25f * a8[k]);
+              }
+            } else {
+              // res_mode 1: nearest-x2 of the half-resolution tensor (skip branch of an up ResBlock)
+              const size_t rpix = p.res_mode == 1 ? ((static_cast<size_t>(n) * (p.H >> 1) + (y >> 1)) * (p.W >> 1) + (x >> 1)) *
+                                                        p.Cout
+                                                  : pix;
+              const uint4* rp = reinterpret_cast<const uint4*>(p.res + rpix + c0);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint4 u = rp[j];
+                const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const float2 f = __half22float2(h2[k]);
+                  v[j * 8 + k * 2] += res_scale * f.x;
+                  v[j * 8 + k * 2 + 1] += res_scale * f.y;
+                }
               }
             }
           }
@@ -835,9 +970,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
       // accumulator fully drained into registers/global: release it to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (lane == 0) {
+        if constexpr (CTA2) mbar_arrive_remote(mapa_shared(smem_u32(&tempty[acc]), 0u));
+        else mbar_arrive(&tempty[acc]);
+      }
 
-      if (!SWAP && p.stats != nullptr && p.NB == 1) {
+      if (!SWAP && BN >= 32 && p.stats != nullptr && p.NB == 1) {
         named_bar_sync(1, kEpThreads);
         for (int e = ep_tid; e < BN; e += kEpThreads) {
           const int cc = e >> 5, j = e & 31;
@@ -853,9 +991,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
   }
 
   __syncthreads();
+  if constexpr (CTA2) cluster_sync_all();  // the peer may still read this CTA's shared memory / arrive on its barriers
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if constexpr (CTA2) tmem_dealloc_2cta(tmem_base, kTmemCols); else tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -866,6 +1005,7 @@ struct ConvOp {
   ConvParams p;
   int BN;
   int MT;
+  int cta2;  // launched as clusters of two CTAs sharing each weight tile (tcgen05 cta_group::2)
   int grid;
   size_t smem_bytes;
 };
@@ -874,7 +1014,10 @@ struct ConvOp {
 
 using namespace asyrp;
 
-static const void* conv_kernel_ptr(int BN, int MT) {
+static const void* conv_kernel_ptr(int BN, int MT, int cta2 = 0) {
+  if (cta2) return reinterpret_cast<const void*>(&conv_gemm_kernel<256, 1, false, true>);
+  if (BN == 16) return MT == 2 ? reinterpret_cast<const void*>(&conv_gemm_kernel<16, 2>)
+                               : reinterpret_cast<const void*>(&conv_gemm_kernel<16, 1>);
   if (BN == 256) return reinterpret_cast<const void*>(&conv_gemm_kernel<256, 1>);
   if (BN == 128) return MT == 2 ? reinterpret_cast<const void*>(&conv_gemm_kernel<128, 2, true>)
                                 : reinterpret_cast<const void*>(&conv_gemm_kernel<128, 1>);
@@ -918,9 +1061,19 @@ struct AsyrpConvDesc {
   int planar_c;
   int up2;  // 1: sub-pixel evaluation of conv3x3(nearest-x2 upsample(src)): see ConvParams::up2
   const float* scales;  // optional DEVICE pointer to (acc_scale, res_scale); overrides the two fields above at run time
+  int res_mode;         // 0: residual has the output geometry; 1: [N][H/2][W/2][Cout], nearest-x2; 2: [N][2H][2W][Cout], avg-pool 2x2
 };
 
 static void conv_tile_shape(int H, int W, int halo, int* TW, int* TH, int* NB);
+
+static int g_cta2 = -1;
+static int cta2_enabled() {  // ASYRP_CTA2=0 / asyrp_set_cta2(0): never use the CTA-pair kernel (A/B measurements)
+  if (g_cta2 < 0) {
+    const char* e = getenv("ASYRP_CTA2");
+    g_cta2 = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return g_cta2;
+}
 
 // A 3x3/s1 conv whose output is at least 8 wide and 16 tall uses 8x16-pixel sub-tiles fed from one halo tile per
 // 64-channel chunk ("halo" geometry, segment mode 3); otherwise three dx-shifted copies (mode 1).
@@ -936,6 +1089,11 @@ static void conv_config(int H, int W, int Cout, int halo, int* BN, int* MT, int 
   int TW, TH, NB;
   conv_tile_shape(H, W, halo, &TW, &TH, &NB);
   constexpr int kNominalBatch = 16;
+  if (Cout == 16) {  // conv_out: 3 / 6 real channels in one 16-wide N tile (an N=64 tile spends 4x the operand reads)
+    *BN = 16;
+    *MT = (NB == 1 && H > 1 && H % (2 * TH) == 0 && W % TW == 0) ? 2 : 1;
+    return;
+  }
   const int tiles_x = (W + TW - 1) / TW, tiles_n = (kNominalBatch + NB - 1) / NB;
   const int cand[5][2] = {{256, 1}, {128, 2}, {128, 1}, {64, 2}, {64, 1}};  // by decreasing operand re-use
   int best = -1, best_tiles = -1;
@@ -1002,7 +1160,9 @@ ASYRP_API int asyrp_conv_stats_tiles_up2(int H, int W, int Cout) {
 ASYRP_API int asyrp_conv_create(const AsyrpConvDesc* d, void** out_op) {
   ASYRP_REQUIRE(d && out_op, "asyrp_conv_create: null argument");
   ASYRP_REQUIRE(d->nseg >= 1 && d->nseg <= kMaxSeg, "asyrp_conv_create: nseg=%d out of range", d->nseg);
-  ASYRP_REQUIRE(d->Cout % 64 == 0, "asyrp_conv_create: Cout=%d must be a multiple of 64", d->Cout);
+  ASYRP_REQUIRE(d->Cout % 64 == 0 || (d->Cout == 16 && d->out_planar != nullptr && d->stats == nullptr &&
+                                      d->residual == nullptr && !d->up2 && !d->weight_batched),
+                "asyrp_conv_create: Cout=%d must be a multiple of 64 (or 16 with a planar fp32 output)", d->Cout);
   ConvOp* op = new ConvOp();
   ConvParams& p = op->p;
   memset(&p, 0, sizeof(p));
@@ -1015,7 +1175,7 @@ ASYRP_API int asyrp_conv_create(const AsyrpConvDesc* d, void** out_op) {
                 d->W);
   ASYRP_REQUIRE(!(d->weight_batched && p.NB != 1), "asyrp_conv_create: batched weights need NB==1");
   if (d->up2)
-    ASYRP_REQUIRE(halo && d->nseg == 1 && d->seg[0].affine == nullptr && !d->weight_batched && !d->out_f32 &&
+    ASYRP_REQUIRE(halo && d->nseg == 1 && !d->weight_batched && !d->out_f32 &&
                       d->out_planar == nullptr && d->out_heads <= 1 && d->a_heads <= 1 && d->residual == nullptr,
                   "asyrp_conv_create: up2 needs one plain 3x3 segment on a source of H %% 16 == 0, W %% 8 == 0");
   p.up2 = d->up2 ? 1 : 0;
@@ -1027,6 +1187,14 @@ ASYRP_API int asyrp_conv_create(const AsyrpConvDesc* d, void** out_op) {
   p.tiles_n = (d->N + p.NB - 1) / p.NB;
   p.m_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
   p.n_tiles = (d->Cout / op->BN) * (p.up2 ? 4 : 1);
+  {
+    // CTA pairs for the 128 px x 256 ch tiles: two horizontally adjacent pixel tiles share each weight tile.  Needs an
+    // even number of pixel tiles per sample (so that the pairing does not depend on the batch) and, at the nominal
+    // batch of 16, enough pairs to occupy the 74 TPCs.  The arithmetic per tile is that of the one-CTA kernel.
+    const int txy = p.tiles_x * p.tiles_y;
+    op->cta2 = cta2_enabled() && op->BN == 256 && op->MT == 1 && p.NB == 1 && txy % 2 == 0 && !d->weight_batched &&
+               d->a_heads <= 1 && d->out_heads <= 1 && (txy / 2) * 16 * p.n_tiles >= 64;
+  }
   {
     // x / dv == umulhi(x, 2^32/dv + 1) for all x with x*dv < 2^32; the largest dividend is the tile count
     const unsigned long long xmax = static_cast<unsigned long long>(p.m_tiles) * p.n_tiles;
@@ -1096,7 +1264,7 @@ ASYRP_API int asyrp_conv_create(const AsyrpConvDesc* d, void** out_op) {
     ASYRP_REQUIRE(bh == 1 || wld >= bh * static_cast<uint64_t>(ktot), "asyrp_conv_create: b_heads needs weight_ld >= heads*K");
     // dim 2 = head (column slices of width K inside a row of weight_ld elements), dim 3 = sample
     uint64_t strides[3] = {wld * 2, (bh > 1 ? static_cast<uint64_t>(ktot) : wbs) * 2, wbs * 2};
-    uint32_t box[4] = {64, static_cast<uint32_t>(op->BN), 1, 1};
+    uint32_t box[4] = {64, static_cast<uint32_t>(op->cta2 ? op->BN / 2 : op->BN), 1, 1};
     int rc = encode_tensor_map(&p.tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, d->weight, dims, strides, box,
                                CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != ASYRP_OK) { delete op; return rc; }
@@ -1136,7 +1304,7 @@ ASYRP_API int asyrp_conv_create(const AsyrpConvDesc* d, void** out_op) {
                 "asyrp_conv_create: out_heads needs N %% heads == 0, no stats / planar output, Cout != 128*odd");
   p.a_stage_bytes = halo ? (((THT + 2) * (p.TW + 2) * 128u + 1023u) / 1024u) * 1024u
                          : (any3 ? THT + 2 : THT) * p.row_bytes;
-  const uint32_t b_stage = op->BN * 128;
+  const uint32_t b_stage = (op->cta2 ? op->BN / 2 : op->BN) * 128;
   // operand rings: everything the 227 KB of shared memory leaves after barriers and the statistics scratch.
   // Activations: 3-4 stages; weights: as deep as fits (<= 16 stages) — small-N tiles issue an MMA group every ~100
   // cycles, so the weight prefetch must run many K steps ahead of the ~1 us TMA latency.
@@ -1168,6 +1336,11 @@ ASYRP_API int asyrp_conv_create(const AsyrpConvDesc* d, void** out_op) {
   p.res_scale = d->res_scale;
   p.acc_scale = d->acc_scale;
   p.scales = d->scales;
+  p.res_mode = d->residual != nullptr ? d->res_mode : 0;
+  ASYRP_REQUIRE(p.res_mode >= 0 && p.res_mode <= 2, "asyrp_conv_create: res_mode %d", d->res_mode);
+  ASYRP_REQUIRE(p.res_mode == 0 || (!p.up2 && p.out_heads == 1 && !d->out_f32 && d->out_planar == nullptr &&
+                                    (p.res_mode == 2 || (d->H % 2 == 0 && d->W % 2 == 0))),
+                "asyrp_conv_create: resampled residual needs a plain NHWC fp16 output (even H, W for nearest-x2)");
   p.out = static_cast<__half*>(d->out);
   p.stats = d->stats;
   op->smem_bytes = 1024 + static_cast<size_t>(p.a_stages) * p.a_stage_bytes +
@@ -1178,8 +1351,12 @@ ASYRP_API int asyrp_conv_create(const AsyrpConvDesc* d, void** out_op) {
   if (sms <= 0) { delete op; return ASYRP_ERR_NO_DEVICE; }
   const int total = p.m_tiles * p.n_tiles;
   op->grid = total < sms ? total : sms;
-  cudaError_t e = cudaFuncSetAttribute(conv_kernel_ptr(op->BN, op->MT), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       227 * 1024);
+  if (op->cta2) {
+    const int pairs = total / 2, clusters = sms / 2;
+    op->grid = 2 * (pairs < clusters ? pairs : clusters);
+  }
+  cudaError_t e = cudaFuncSetAttribute(conv_kernel_ptr(op->BN, op->MT, op->cta2),
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) {
     set_error("asyrp_conv_create: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     delete op;
@@ -1195,18 +1372,25 @@ ASYRP_API int asyrp_conv_launch(void* handle, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   void* args[] = {&op->p};
   cudaLaunchConfig_t cfg = {};
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   cfg.gridDim = dim3(op->grid);
   cfg.blockDim = dim3(kNumThreads);
   cfg.dynamicSmemBytes = op->smem_bytes;
   cfg.stream = st;
   cfg.attrs = attr;
   if (pdl_enabled()) {
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.numAttrs = 1;
+    attr[cfg.numAttrs].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[cfg.numAttrs].val.programmaticStreamSerializationAllowed = 1;
+    ++cfg.numAttrs;
   }
-  ASYRP_CHECK_CUDA(cudaLaunchKernelExC(&cfg, conv_kernel_ptr(op->BN, op->MT), args));
+  if (op->cta2) {
+    attr[cfg.numAttrs].id = cudaLaunchAttributeClusterDimension;
+    attr[cfg.numAttrs].val.clusterDim.x = 2;
+    attr[cfg.numAttrs].val.clusterDim.y = 1;
+    attr[cfg.numAttrs].val.clusterDim.z = 1;
+    ++cfg.numAttrs;
+  }
+  ASYRP_CHECK_CUDA(cudaLaunchKernelExC(&cfg, conv_kernel_ptr(op->BN, op->MT, op->cta2), args));
   return ASYRP_OK;
 }
 
@@ -1221,5 +1405,13 @@ ASYRP_API int asyrp_conv_set_scales(void* handle, float acc_scale, float res_sca
 }
 
 ASYRP_API void asyrp_conv_destroy(void* handle) { delete static_cast<ConvOp*>(handle); }
+
+// CTA-pair (tcgen05 cta_group::2) variant of the 128 px x 256 ch tile: on by default; affects ops created afterwards
+ASYRP_API int asyrp_set_cta2(int enabled) {
+  g_cta2 = enabled ? 1 : 0;
+  return ASYRP_OK;
+}
+// 1 if `op` runs as CTA pairs
+ASYRP_API int asyrp_conv_is_cta2(void* handle) { return handle ? static_cast<ConvOp*>(handle)->cta2 : 0; }
 
 }  // extern "C"

@@ -128,6 +128,13 @@ def pack_weights(arch: Arch, sd, device, n_delta):
         W[p + ".w1"] = torch.cat(parts, dim=1).contiguous().to(device)
         w2 = ops.pack_conv_weight(sd[p + c2 + ".weight"].detach().float())
         b2 = sd[p + c2 + ".bias"].detach().float().cpu()
+        if layer.resample != "none":
+            # ADM up / down ResBlock (channels unchanged): the skip branch is x resampled, added by the epilogue through
+            # an index-mapped residual read; conv1 of an up block runs on the source image as sub-pixel phases
+            assert layer.cin == layer.cout and not layer.split
+            W[p + ".w2r"] = w2.contiguous().to(device)
+            if layer.resample == "up":
+                W[p + ".w1_up"] = ops.pack_upconv_weight(w1).to(device)
         if layer.cin != layer.cout:
             # 1x1 shortcut on the raw (possibly concatenated) input: extra K columns of the same GEMM
             w2 = torch.cat([w2, ops.pack_conv_weight(sd[p + sc + ".weight"].detach().float())], dim=1)
@@ -164,11 +171,11 @@ def pack_weights(arch: Arch, sd, device, n_delta):
         for layer in stage:
             {Res: res, Attn: attn, Resample: resample}[type(layer)](layer)
 
-    # conv_out: output channels padded to one 64-wide N tile; only [0, out_ch) is stored (fp32 planar)
+    # conv_out: output channels padded to one 16-wide N tile; only [0, out_ch) is stored (fp32 planar)
     w = sd[arch.conv_out + ".weight"].detach().float().cpu()
-    wpad = torch.zeros(64, *w.shape[1:])
+    wpad = torch.zeros(16, *w.shape[1:])
     wpad[: w.shape[0]] = w
-    bpad = torch.zeros(64)
+    bpad = torch.zeros(16)
     bpad[: w.shape[0]] = sd[arch.conv_out + ".bias"].detach().float().cpu()
     W["conv_out.w"], W["conv_out.b"] = pk(wpad), f32(bpad)
     W["norm_out.g"], W["norm_out.be"] = f32(sd[arch.norm_out + ".weight"]), f32(sd[arch.norm_out + ".bias"])
@@ -257,7 +264,7 @@ class Plan:
         return out
 
     def _conv(self, segs, weight, Cout, H, W, ebias=None, ebias_stride=0, residual=None, res_scale=1.0,
-              acc_scale=1.0, stats=True, planar=None, algo_flops=None, up2=False, scales=None):
+              acc_scale=1.0, stats=True, planar=None, algo_flops=None, up2=False, scales=None, res_mode=0):
         """H, W: output geometry (for up2 = twice the source's)"""
         out = None
         if planar is None:
@@ -267,7 +274,7 @@ class Plan:
         op = ops.ConvOp([(sg[0].t,) + sg[1:] for sg in segs], weight, out=out.t if out else None, ebias=ebias,
                         ebias_stride=ebias_stride, residual=residual.t if residual is not None else None,
                         res_scale=res_scale, acc_scale=acc_scale, stats=out.stats if out else None,
-                        out_planar=planar, out_shape=(self.N, H, W, Cout), up2=up2, scales=scales)
+                        out_planar=planar, out_shape=(self.N, H, W, Cout), up2=up2, scales=scales, res_mode=res_mode)
         ktot = weight.shape[-1]
         flops = algo_flops if algo_flops is not None else 2.0 * self.N * H * W * Cout * ktot
         nbytes = 2.0 * (sum(sg[0].t.numel() for sg in segs) + weight.numel() + self.N * H * W * Cout
@@ -310,13 +317,22 @@ class Plan:
         eoff = eng.emb_off[p]
         mode = {"none": RESAMPLE_NONE, "up": RESAMPLE_UP2, "down": RESAMPLE_AVGPOOL2}[layer.resample]
         aff1 = self._gn(srcs, W[p + ".g1"], W[p + ".be1"])
-        xr, a1 = None, None
+        xr, a1, res_mode, up_fused = None, None, 0, False
         if mode != RESAMPLE_NONE:
             # ADM up/down block: the resample sits between SiLU and the conv, and the skip branch is resampled too
-            # (unet.py:279-284) -> materialise both with the pointwise kernel
-            a1 = self._apply(srcs, aff1, 1, mode)
-            xr = self._apply(srcs, None, 0, mode)
-            segs1, H, Wd = [(a1, MODE_3x3)], a1.H, a1.W
+            # (unet.py:279-284).  The skip branch is never materialised: conv2's epilogue reads x through the resample
+            # index map (res_mode).  Up: conv1 = conv(nearest-x2(silu(GN(x)))) runs on the source image as four
+            # sub-pixel phases with the GN-apply + SiLU fused into the operand.  Down: the pooled activation is
+            # materialised (a quarter of the input's size).
+            src = srcs[0]
+            res_mode = 1 if mode == RESAMPLE_UP2 else 2
+            up_fused = mode == RESAMPLE_UP2 and src.H >= 16 and ops.conv_stats_tiles_up2(src.H, src.W, layer.cout) > 0
+            if up_fused:
+                H, Wd = 2 * src.H, 2 * src.W
+                segs1 = [(src, MODE_3x3, aff1, 0, 1)]
+            else:
+                a1 = self._apply(srcs, aff1, 1, mode)
+                segs1, H, Wd = [(a1, MODE_3x3)], a1.H, a1.W
         else:
             segs1, H, Wd = self._fused(srcs, MODE_3x3, aff1, 1), srcs[0].H, srcs[0].W
         if ddpm:
@@ -324,7 +340,11 @@ class Plan:
                               ebias=self.emb_all[:, eoff:eoff + layer.cout], ebias_stride=eng.emb_total)
             aff2 = self._gn([h], W[p + ".g2"], W[p + ".be2"])
         else:
-            h, _ = self._conv(segs1, W[p + ".w1"], layer.cout, H, Wd, ebias=W[p + ".b1"])
+            if up_fused:
+                h, _ = self._conv(segs1, W[p + ".w1_up"], layer.cout, H, Wd, ebias=W[p + ".b1"], up2=True,
+                                  algo_flops=2.0 * self.N * H * Wd * layer.cout * 9 * layer.cin)
+            else:
+                h, _ = self._conv(segs1, W[p + ".w1"], layer.cout, H, Wd, ebias=W[p + ".b1"])
             # GN(h)*(1+scale)+shift, [scale | shift] = Linear(SiLU(emb))  (unet.py:287-294)
             aff2 = self._gn([h], W[p + ".g2"], W[p + ".be2"], self.emb_all[:, eoff:eoff + 2 * layer.cout],
                             eng.emb_total)
@@ -332,7 +352,10 @@ class Plan:
         if a1 is not None:
             self._free(a1)
         segs2 = self._fused([h], MODE_3x3, aff2, 1)
-        if layer.cin != layer.cout:
+        if res_mode:
+            out, _ = self._conv(segs2, W[p + ".w2r"], layer.cout, H, Wd, ebias=W[p + ".b2"], residual=srcs[0],
+                                res_mode=res_mode)
+        elif layer.cin != layer.cout:
             out, _ = self._conv(segs2 + [(s_, MODE_1x1) for s_ in srcs], W[p + ".w2"], layer.cout, H, Wd,
                                 ebias=W[p + ".b2"])
         else:
@@ -535,7 +558,7 @@ class Plan:
             h = self._run_stage(stage, h, skip=self.hs[idx], keep_input=(si == 0))
             idx -= 1
         aff = self._gn([h], W["norm_out.g"], W["norm_out.be"])
-        self._conv(self._fused([h], MODE_3x3, aff, 1), W["conv_out.w"], 64, h.H, h.W, ebias=W["conv_out.b"],
+        self._conv(self._fused([h], MODE_3x3, aff, 1), W["conv_out.w"], 16, h.H, h.W, ebias=W["conv_out.b"],
                    stats=False, planar=out_planar, algo_flops=2.0 * self.N * h.H * h.W * a.out_ch * 9 * h.C)
         self.pool.release(aff)
         self._free(h)

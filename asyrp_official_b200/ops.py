@@ -87,7 +87,7 @@ class ConvOp:
 
     def __init__(self, segs, weight, out=None, ebias=None, ebias_stride=0, residual=None, res_scale=1.0,
                  acc_scale=1.0, stats=None, out_planar=None, out_shape=None, weight_batched=False, a_heads=1,
-                 b_heads=1, out_heads=1, up2=False, scales=None):
+                 b_heads=1, out_heads=1, up2=False, scales=None, res_mode=0):
         lib = _lib.load()
         segs = [tuple(sg) + (None, 0, 0) * (len(sg) == 2) for sg in segs]
         srcs = [sg[0] for sg in segs]
@@ -136,6 +136,7 @@ class ConvOp:
         d.ebias_stride = ebias_stride
         d.residual = residual.data_ptr() if residual is not None else None
         d.res_scale, d.acc_scale = res_scale, acc_scale
+        d.res_mode = int(res_mode)  # 1: residual is [N][H/2][W/2][Cout] (nearest-x2); 2: [N][2H][2W][Cout] (avg-pool)
         if scales is not None:  # device-side (acc_scale, res_scale): overrides the two values above at run time
             assert scales.dtype == torch.float32 and scales.is_cuda and scales.numel() >= 2 and scales.is_contiguous()
             d.scales = scales.data_ptr()
@@ -155,6 +156,11 @@ class ConvOp:
         check(self._lib.asyrp_conv_launch(self._h, _stream()), "asyrp_conv_launch")
 
     __call__ = launch
+
+    @property
+    def cta2(self):
+        """runs as CTA pairs (tcgen05 cta_group::2)"""
+        return bool(self._lib.asyrp_conv_is_cta2(self._h))
 
     def set_scales(self, acc_scale, res_scale):
         check(self._lib.asyrp_conv_set_scales(self._h, acc_scale, res_scale), "asyrp_conv_set_scales")

@@ -14,8 +14,8 @@ broadcast).
 Prints ONE JSON line (rank 0):
   value          device-timed (CUDA events, inputs resident in HBM), whole job
   e2e            through Asyrp.edit_batch with pinned host buffers (H2D of x_T, D2H of x_0 inside the timed region)
-  roofline       the tcgen05 conv kernel: algorithmic conv FLOPs of one edit-step UNet evaluation / device time of a
-                 CUDA graph holding exactly those conv launches (replayed back to back, CUDA events), vs the measured
+  roofline       the tcgen05 conv kernel: algorithmic conv FLOPs of one edit-step UNet evaluation / (device time of the
+                 captured evaluation minus that of its non-conv launches; CUDA graphs, CUDA events), vs the measured
                  sustained bf16 cuBLAS peak; `traffic` is read from the committed ncu capture under profiles/
   parity         engine vs the REFERENCE's own output (tests/golden/, written by tests/golden/make_golden.py) on the
                  same weights / x_T / noise, for this workload
@@ -474,29 +474,35 @@ def main():
             dist.barrier()
             dist.destroy_process_group()
         return
-    # ---- roofline of the dominant kernel (tcgen05 implicit-GEMM conv): device time of a graph holding exactly the
-    # conv launches of one edit-step evaluation, replayed back to back (CUDA events around the replays)
+    # ---- roofline of the dominant kernel (tcgen05 implicit-GEMM conv), timed inside the captured evaluation:
+    # eval_ms   = device time of a CUDA graph holding ALL launches of one edit-step UNet evaluation (valid data flow,
+    #             the clocks / power state of the real trajectory), replayed back to back, CUDA events around the replays
+    # other_ms  = the same for a graph holding every NON-conv launch of that evaluation
+    # conv_ms   = eval_ms - other_ms (launch gaps are charged to the conv kernel)
+    # A graph of the conv launches alone is NOT used: without the GroupNorm finalise launches between them the
+    # activations degenerate to NaN within a few replays, the board draws less power, clocks rise from ~1.57 to
+    # 1.97 GHz and the kernel reads 25-30 % faster than it runs on real data (measured: 10.1 vs 13.1 ms).
     peak_tf, peak_gbs, burst_tf, peak_src = peaks()
     P = eng.plan(batch)
-    P.emb_all.copy_(eng.graphs[next(reversed(eng.graphs))]["emb_table"][0])
     seq_l = P.launches(True, temb=False)
     convs = [L for L in seq_l if L.kind == "conv"]
-    ms_conv = P.graph_time(convs)
+    others = [L for L in seq_l if L.kind != "conv"]
     ms_eval = P.graph_time(seq_l)
+    ms_other = P.graph_time(others)
+    ms_conv = ms_eval - ms_other
     conv_flops = sum(L.flops for L in convs)
     conv_tf = conv_flops / (ms_conv * 1e-3) / 1e12
     conv_exec_tf = sum(L.exec_flops for L in convs) / (ms_conv * 1e-3) / 1e12
     step_tf = value / args.gpus * f_img(key, traj_steps, sch.n_edit) / 1e12
     kinds = {}
-    for L in seq_l:
+    for L in others:
         kinds.setdefault(L.kind, []).append(L)
     kern = {}
     for k, ls in kinds.items():
-        if k == "conv":
-            continue
         ms_k = P.graph_time(ls, reps=10, warm=2)
         nb = sum(L.nbytes for L in ls)
         kern[k] = {"ms": round(ms_k, 3), "launches": len(ls), "gbs": round(nb / (ms_k * 1e-3) / 1e9, 1) if nb else None}
+    P.graph_time(seq_l, reps=1, warm=0)  # leave valid activations behind
     traffic, traffic_src, traffic_kernel = ncu_traffic()
     roofline = {"bound": "tensor", "kernel": "conv_gemm_kernel (tcgen05 implicit GEMM, fp16 operands, fp32 accumulate)",
                 "achieved": round(conv_tf, 1), "peak": peak_tf, "unit": "TFLOP/s", "frac": round(conv_tf / peak_tf, 4),
@@ -508,10 +514,11 @@ def main():
                 "executed_tflops": round(conv_exec_tf, 1),
                 "executed_note": "the Upsample.conv launches issue 4/9 of their algorithmic MACs (sub-pixel phases); "
                                  "every other conv launch executes exactly its algorithmic FLOPs",
-                "how": f"sum of algorithmic conv FLOPs ({conv_flops / 1e12:.2f} TFLOP) of the {len(convs)} conv launches "
-                       f"of one edit-step UNet evaluation at batch {batch} / device time of a CUDA graph holding exactly "
-                       f"those launches ({ms_conv:.3f} ms per replay, 20 back-to-back replays, CUDA events)",
-                "conv_ms": round(ms_conv, 3), "eval_ms": round(ms_eval, 3),
+                "how": f"algorithmic conv FLOPs ({conv_flops / 1e12:.2f} TFLOP) of the {len(convs)} conv launches of one "
+                       f"edit-step UNet evaluation at batch {batch} / (device time of the captured evaluation, "
+                       f"{ms_eval:.3f} ms, minus that of its {len(others)} non-conv launches, {ms_other:.3f} ms); CUDA "
+                       "graphs replayed 20x back to back, CUDA events around the replays",
+                "conv_ms": round(ms_conv, 3), "eval_ms": round(ms_eval, 3), "other_ms": round(ms_other, 3),
                 "conv_share_of_step": round(ms_conv / ms_eval, 4), "launches_per_edit_eval": len(seq_l),
                 "whole_step": {"achieved": round(step_tf, 1), "frac": round(step_tf / peak_tf, 4),
                                "f_img_tflop": round(f_img(key, traj_steps, sch.n_edit) / 1e12, 2)},

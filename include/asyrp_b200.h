@@ -30,8 +30,9 @@ const char* asyrp_last_error(void);
 /* Programmatic dependent launch: every kernel of the library begins with griddepcontrol.launch_dependents and
  * executes griddepcontrol.wait before its first global-memory access, and is launched with the
  * programmaticStreamSerialization attribute, so consecutive kernels of a stream (or of a captured graph) overlap
- * launch latency and prologue with the predecessor's tail.  Results are unchanged.  Default on (ASYRP_PDL=0 in the
- * environment or asyrp_set_pdl(0) turns it off).  The reference's equivalent is the implicit stream order of
+ * launch latency and prologue with the predecessor's tail.  Results are unchanged.  Default off: inside the captured
+ * trajectory graph it measured neutral (443.0 vs 448.7 ms); ASYRP_PDL=1 in the environment or asyrp_set_pdl(1) turns
+ * it on for eager, launch-bound callers.  The reference's equivalent is the implicit stream order of
  * PyTorch's eager launches (one or more library kernels per line of models/ddpm/diffusion.py:473-580). */
 int asyrp_set_pdl(int enabled);
 int asyrp_get_pdl(void);
@@ -70,7 +71,7 @@ typedef struct AsyrpConvSeg {
 } AsyrpConvSeg;
 
 typedef struct AsyrpConvDesc {
-  int N, H, W, Cout;     /* output geometry; Cout multiple of 64 */
+  int N, H, W, Cout;     /* output geometry; Cout multiple of 64 (or 16 with out_planar: the conv_out tile) */
   int nseg;              /* 1..3 */
   AsyrpConvSeg seg[3];
   const void* weight;    /* fp16 [Cout][K] ([N][Cout][K] if weight_batched), K = sum_seg taps*C */
@@ -96,12 +97,17 @@ typedef struct AsyrpConvDesc {
    * conv3x3(F.interpolate(src, scale_factor=2, mode="nearest")), evaluated on the SOURCE image as four sub-pixel
    * phases: N/H/W are the source geometry (H%16==0, W%8==0), out is [N][2H][2W][Cout], one ASYRP_CONV_3x3 segment,
    * weight is fp16 [4*Cout][4*C] (phase-major rows, 2x2 taps x C; the 3x3 taps that fall on one source pixel are
-   * pre-summed), stats has asyrp_conv_stats_tiles_up2() slots.  4/9 of the MACs, no upsampled tensor. */
+   * pre-summed), stats has asyrp_conv_stats_tiles_up2() slots.  4/9 of the MACs, no upsampled tensor.  With a fused
+   * affine on the segment this is also in_layers of the ADM ResBlock(up=True): conv(nearest-x2(silu(GN(x)))). */
   int up2;
   /* optional DEVICE pointer to two floats (acc_scale, res_scale) read by the kernel at run time instead of the
    * by-value fields: the DeltaBlock coefficients hs_coeff are per-call arguments of forward()
    * (ddpm/diffusion.py:512-516), so one captured trajectory graph serves every coefficient tuple */
   const float* scales;
+  /* residual geometry: 0 = that of the output; 1 = [N][H/2][W/2][Cout], read through nearest-x2 upsampling; 2 =
+   * [N][2H][2W][Cout], read through a 2x2 average pool — the skip branch x_upd(x) of the ADM ResBlock(up / down)
+   * (improved_ddpm/unet.py:279-284,297), so that the resampled copy of x is never materialised */
+  int res_mode;
 } AsyrpConvDesc;
 
 /* number of tile slots of the stats buffer of a conv with this output geometry; has_3x3: the conv has an
@@ -109,6 +115,11 @@ typedef struct AsyrpConvDesc {
 int asyrp_conv_stats_tiles(int H, int W, int Cout, int has_3x3);
 /* the same for an up2 conv over an H x W source image (0 if the geometry is unsupported) */
 int asyrp_conv_stats_tiles_up2(int H, int W, int Cout);
+/* CTA pairs: convs whose tile is 128 pixels x 256 channels run as clusters of two CTAs (the two SMs of a TPC) that share
+ * every weight tile through `tcgen05.mma.cta_group::2` (M = 256): each SM loads half of the weight rows.  Bit-identical
+ * to the one-CTA kernel.  On by default (ASYRP_CTA2=0 or asyrp_set_cta2(0) disables it for ops created afterwards). */
+int asyrp_set_cta2(int enabled);
+int asyrp_conv_is_cta2(void* op);
 int asyrp_conv_create(const AsyrpConvDesc* desc, void** op); /* encodes TMA descriptors; host only */
 int asyrp_conv_launch(void* op, void* stream);
 int asyrp_conv_set_scales(void* op, float acc_scale, float res_scale); /* hs_coeff of forward(), diffusion.py:512-516 */

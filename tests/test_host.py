@@ -183,7 +183,7 @@ def test_weight_packing_layout():
                         w = sd[key]
                         assert torch.equal(W[p + ".w1"][:, :9 * c0].float().reshape(layer.cout, 3, 3, c0),
                                            w[:, :c0].permute(0, 2, 3, 1).to(torch.float16).float())
-        assert W["conv_in.w"].shape[1] == 9 * 64 and W["conv_out.w"].shape[0] == 64
+        assert W["conv_in.w"].shape[1] == 9 * 64 and W["conv_out.w"].shape[0] == 16
 
 
 def test_upconv_subpixel_weights():

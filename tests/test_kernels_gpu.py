@@ -443,3 +443,158 @@ def test_upsample_conv_subpixel(cuda_device, N, H, W, C):
     st = stats.sum(dim=1).cpu().double()
     sref = _stats_ref(ref)
     assert (st - sref).abs().max().item() <= 3e-3 * sref.abs().max().item() + 1e-3
+
+
+@pytest.mark.parametrize("case", ["plain", "fused_shortcut", "stride2", "cout512", "up2"])
+def test_cta_pair_kernel_matches_reference_and_one_cta_kernel(cuda_device, case):
+    """tcgen05 cta_group::2 variant of the 128 px x 256 ch tile (two CTAs of a cluster share every weight tile): against
+    the fp64 formula AND bit-for-bit against the one-CTA kernel on the same operands"""
+    ops = _ops()
+    lib = ops._lib.load()
+    g = torch.Generator().manual_seed(31)
+    N = 3
+    kw, ref, shape = {}, None, None
+    if case == "plain":
+        H = W = 32
+        x, w = _rand((N, 256, H, W), g), _rand((256, 256, 3, 3), g, 1.0 / math.sqrt(9 * 256))
+        eb, res = _rand((N, 256), g), _rand((N, 256, H, W), g)
+        ref = 0.75 * (F.conv2d(_h(x), _h(w), padding=1) + eb.double()[:, :, None, None]) + 1.5 * _h(res)
+        segs = [(_nhwc_half(x, cuda_device), ops.MODE_3x3)]
+        wp = ops.pack_conv_weight(w)
+        kw = dict(ebias=eb.to(cuda_device), ebias_stride=256, residual=_nhwc_half(res, cuda_device), res_scale=1.5,
+                  acc_scale=0.75)
+        shape = (N, H, W, 256)
+    elif case == "fused_shortcut":
+        H = W = 32
+        h, x1, x2 = _rand((N, 256, H, W), g), _rand((N, 256, H, W), g), _rand((N, 128, H, W), g)
+        aff = torch.stack([_rand((N, 256), g) * 0.5 + 1.0, _rand((N, 256), g) * 0.5], dim=-1).contiguous()
+        w3 = _rand((256, 256, 3, 3), g, 1.0 / math.sqrt(9 * 256))
+        w1 = _rand((256, 384, 1, 1), g, 1.0 / math.sqrt(384))
+        y = _h(h) * aff[..., 0].double()[:, :, None, None] + aff[..., 1].double()[:, :, None, None]
+        y = _h((y * torch.sigmoid(y)).float())
+        ref = F.conv2d(y, _h(w3), padding=1) + F.conv2d(torch.cat([_h(x1), _h(x2)], 1), _h(w1))
+        segs = [(_nhwc_half(h, cuda_device), ops.MODE_3x3, aff.to(cuda_device), 0, 1),
+                (_nhwc_half(x1, cuda_device), ops.MODE_1x1), (_nhwc_half(x2, cuda_device), ops.MODE_1x1)]
+        wp = torch.cat([ops.pack_conv_weight(w3), ops.pack_conv_weight(w1[:, :256]), ops.pack_conv_weight(w1[:, 256:])], 1)
+        shape = (N, H, W, 256)
+    elif case == "stride2":
+        x, w = _rand((N, 256, 64, 64), g), _rand((256, 256, 3, 3), g, 1.0 / math.sqrt(9 * 256))
+        ref = F.conv2d(F.pad(_h(x), (0, 1, 0, 1)), _h(w), stride=2)
+        segs = [(_nhwc_half(x, cuda_device), ops.MODE_3x3_S2)]
+        wp = ops.pack_conv_weight(w)
+        shape = (N, 32, 32, 256)
+    elif case == "cout512":
+        H = W = 32
+        x, w = _rand((N, 128, H, W), g), _rand((512, 128, 3, 3), g, 1.0 / math.sqrt(9 * 128))
+        ref = F.conv2d(_h(x), _h(w), padding=1)
+        segs = [(_nhwc_half(x, cuda_device), ops.MODE_3x3)]
+        wp = ops.pack_conv_weight(w)
+        shape = (N, H, W, 512)
+    else:
+        H = W = 16
+        x, w = _rand((N, 256, H, W), g), _rand((256, 256, 3, 3), g, 1.0 / math.sqrt(9 * 256))
+        ref = F.conv2d(F.interpolate(_h(x), scale_factor=2.0, mode="nearest"), w.double(), padding=1)
+        segs = [(_nhwc_half(x, cuda_device), ops.MODE_3x3)]
+        wp = ops.pack_upconv_weight(w)
+        kw = dict(up2=True)
+        shape = (N, 2 * H, 2 * W, 256)
+    outs = []
+    try:
+        for on in (1, 0):
+            lib.asyrp_set_cta2(on)
+            out = torch.zeros(shape, dtype=torch.float16, device=cuda_device)
+            tiles = ops.conv_stats_tiles_up2(16, 16, 256) if case == "up2" else \
+                ops.conv_stats_tiles(shape[1], shape[2], shape[3], int(case in ("plain", "fused_shortcut", "cout512")))
+            stats = torch.zeros(N, tiles, shape[3] // 2, 2, dtype=torch.float32, device=cuda_device)
+            op = ops.ConvOp(segs, wp.contiguous().to(cuda_device), out=out, stats=stats, **kw)
+            assert op.cta2 == bool(on), f"{case}: CTA-pair selection {op.cta2} with cta2={on}"
+            op.launch()
+            op.launch()
+            torch.cuda.synchronize()
+            outs.append((out, stats))
+    finally:
+        lib.asyrp_set_cta2(1)
+    _check(_from_nhwc(outs[0][0]), ref, 2.5e-3, f"cta pair {case}")
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]), "CTA-pair kernel != one-CTA kernel"
+
+
+@pytest.mark.parametrize("Co,fused", [(3, False), (6, True)])
+def test_conv_out_narrow_tile(cuda_device, Co, fused):
+    """conv_out as a 16-wide N tile (BN=16): 3 / 6 real channels, fp32 planar store, bias, optional fused GN+SiLU"""
+    ops = _ops()
+    g = torch.Generator().manual_seed(41)
+    N, H, W, C = 2, 32, 32, 128
+    x = _rand((N, C, H, W), g)
+    w = torch.zeros(16, C, 3, 3)
+    w[:Co] = _rand((Co, C, 3, 3), g, 1.0 / math.sqrt(9 * C))
+    b = torch.zeros(16)
+    b[:Co] = _rand((Co,), g)
+    y = _h(x)
+    seg = (_nhwc_half(x, cuda_device), ops.MODE_3x3)
+    if fused:
+        aff = torch.stack([_rand((N, C), g) * 0.5 + 1.0, _rand((N, C), g) * 0.5], dim=-1).contiguous()
+        y = y * aff[..., 0].double()[:, :, None, None] + aff[..., 1].double()[:, :, None, None]
+        y = _h((y * torch.sigmoid(y)).float())
+        seg = seg + (aff.to(cuda_device), 0, 1)
+    ref = F.conv2d(y, _h(w[:Co]), padding=1) + b[:Co].double()[None, :, None, None]
+    outp = torch.zeros(N, Co, H, W, dtype=torch.float32, device=cuda_device)
+    op = ops.ConvOp([seg], ops.pack_conv_weight(w).to(cuda_device), out_shape=(N, H, W, 16), ebias=b.to(cuda_device),
+                    out_planar=outp)
+    op.launch()
+    op.launch()
+    torch.cuda.synchronize()
+    _check(outp.cpu(), ref, 2.5e-3 if fused else 2e-5, "narrow conv_out tile")
+
+
+@pytest.mark.parametrize("C,H,mode", [(128, 32, "up"), (256, 32, "up"), (128, 64, "down"), (256, 32, "down"), (512, 16, "down"),
+                                      (128, 16, "up"), (128, 64, "up")])
+def test_resampled_residual_in_the_epilogue(cuda_device, C, H, mode):
+    """skip branch of the ADM ResBlock(up / down) (improved_ddpm/unet.py:279-284,297): out = conv3x3(a) + resample(x),
+    x read by the epilogue through the nearest-x2 / 2x2-average index map (AsyrpConvDesc.res_mode), both epilogues
+    (swapped 128-channel tile and generic / CTA-pair tile)"""
+    ops = _ops()
+    g = torch.Generator().manual_seed(51)
+    N = 2
+    a = _rand((N, C, H, H), g)
+    w = _rand((C, C, 3, 3), g, 1.0 / math.sqrt(9 * C))
+    b = _rand((C,), g)
+    if mode == "up":
+        x = _rand((N, C, H // 2, H // 2), g)
+        skip = F.interpolate(_h(x), scale_factor=2, mode="nearest")
+    else:
+        x = _rand((N, C, 2 * H, 2 * H), g)
+        skip = F.avg_pool2d(_h(x), 2)
+    ref = F.conv2d(_h(a), _h(w), padding=1) + b.double()[None, :, None, None] + skip
+    out = torch.empty(N, H, H, C, dtype=torch.float16, device=cuda_device)
+    stats = ops.new_stats(N, H, H, C, cuda_device, True)
+    op = ops.ConvOp([(_nhwc_half(a, cuda_device), ops.MODE_3x3)], ops.pack_conv_weight(w).to(cuda_device), out=out,
+                    ebias=b.to(cuda_device), residual=_nhwc_half(x, cuda_device), stats=stats,
+                    res_mode=1 if mode == "up" else 2)
+    op.launch()
+    torch.cuda.synchronize()
+    _check(_from_nhwc(out), ref, 1.5e-3, f"resampled residual {mode}")
+    st = stats.sum(dim=1).cpu().double()
+    sref = _stats_ref(ref)
+    assert (st - sref).abs().max().item() <= 2e-3 * sref.abs().max().item() + 1e-3
+
+
+@pytest.mark.parametrize("C,H", [(128, 32), (256, 16)])
+def test_subpixel_upconv_with_fused_groupnorm_silu(cuda_device, C, H):
+    """in_layers of the ADM ResBlock(up=True): conv3x3(nearest-x2(silu(GN(x)))) on the source image — sub-pixel phases
+    with the affine + SiLU applied to the operand tile in shared memory (improved_ddpm/unet.py:224-228,279-283)"""
+    ops = _ops()
+    g = torch.Generator().manual_seed(52)
+    N = 2
+    x = _rand((N, C, H, H), g) * 1.5 + 0.2
+    aff = torch.stack([_rand((N, C), g) * 0.5 + 1.0, _rand((N, C), g) * 0.5], dim=-1).contiguous()
+    w = _rand((C, C, 3, 3), g, 1.0 / math.sqrt(9 * C))
+    y = _h(x) * aff[..., 0].double()[:, :, None, None] + aff[..., 1].double()[:, :, None, None]
+    y = _h((y * torch.sigmoid(y)).float())
+    ref = F.conv2d(F.interpolate(y, scale_factor=2.0, mode="nearest"), w.double(), padding=1)
+    out = torch.zeros(N, 2 * H, 2 * H, C, dtype=torch.float16, device=cuda_device)
+    stats = torch.zeros(N, ops.conv_stats_tiles_up2(H, H, C), C // 2, 2, dtype=torch.float32, device=cuda_device)
+    op = ops.ConvOp([(_nhwc_half(x, cuda_device), ops.MODE_3x3, aff.to(cuda_device), 0, 1)],
+                    ops.pack_upconv_weight(w).to(cuda_device), out=out, stats=stats, up2=True)
+    op.launch()
+    torch.cuda.synchronize()
+    _check(_from_nhwc(out), ref, 3e-3, "fused up2 conv")
