@@ -180,14 +180,22 @@ __device__ __forceinline__ void transform_fast(uint32_t base, uint32_t vld, uint
 #pragma unroll
   for (int k = 0; k < U; ++k) {
     __half2* h2 = reinterpret_cast<__half2*>(&u[k]);
+    float v[8];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      float2 f = __half22float2(h2[e]);
-      f.x = fmaf(ca[2 * e], f.x, cb[2 * e]);
-      f.y = fmaf(ca[2 * e + 1], f.y, cb[2 * e + 1]);
-      if (act) { f.x = silu_fast(f.x); f.y = silu_fast(f.y); }
-      h2[e] = __floats2half2_rn(f.x, f.y);
+      const float2 f = __half22float2(h2[e]);
+      v[2 * e] = fmaf(ca[2 * e], f.x, cb[2 * e]);
+      v[2 * e + 1] = fmaf(ca[2 * e + 1], f.y, cb[2 * e + 1]);
     }
+    if (act == 1) {  // one reciprocal per four activations (the transform is special-function bound)
+      silu4_fast(v[0], v[1], v[2], v[3]);
+      silu4_fast(v[4], v[5], v[6], v[7]);
+    } else if (act == 2) {  // one reciprocal per activation (A/B reference)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = silu_fast(v[e]);
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) h2[e] = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
     if (CHK && !((img >> k) & 1u)) u[k] = make_uint4(0u, 0u, 0u, 0u);
   }
 #pragma unroll

@@ -13,12 +13,22 @@ A `UNetEngine` owns, for one UNet (arch.Arch + a state dict in the reference's n
 Everything computed here is a kernel of libasyrp_b200.so; torch provides device memory, streams and graphs.
 """
 import math
+import os
 
 import torch
 
 from . import ops
 from .arch import Arch, Attn, Res, Resample
 from .ops import MODE_1x1, MODE_3x3, MODE_3x3_S2, RESAMPLE_AVGPOOL2, RESAMPLE_NONE, RESAMPLE_UP2
+
+
+# ASYRP_DUAL_STREAM=0: run the two decoder passes of an edit step one after the other (A/B measurements)
+DUAL_STREAM = os.environ.get("ASYRP_DUAL_STREAM", "1") != "0"
+# ResBlock identity skips x + h ride conv2's K loop as an identity weight block (C extra MACs per output, exact: fp16 x
+# times 1.0 into the fp32 accumulator).  ASYRP_SKIP_AS_K=0 reads x in the epilogue instead.  A/B on one B200 (round 2,
+# ABAB order): 35.57 / 35.51 img/s with the K columns vs 34.39 / 34.30 with the epilogue read — the scattered fp16
+# residual loads of the swapped-operand epilogue cost more than 11 % extra MMAs on those convs.
+SKIP_AS_K = os.environ.get("ASYRP_SKIP_AS_K", "1") != "0"
 
 
 class Act:
@@ -140,8 +150,11 @@ def pack_weights(arch: Arch, sd, device, n_delta):
             w2 = torch.cat([w2, ops.pack_conv_weight(sd[p + sc + ".weight"].detach().float())], dim=1)
             b2 = b2 + sd[p + sc + ".bias"].detach().float().cpu()
         else:
-            # identity skip: x + h as K columns with an identity weight block (exact: fp16 x times 1.0 into the fp32
-            # accumulator) — the residual rides the TMA/tensor-core pipeline instead of scattered epilogue loads
+            # identity skip x + h: a residual read in conv2's epilogue (W[".w2r"]); or (ASYRP_SKIP_AS_K=1) K columns with
+            # an identity weight block (exact: fp16 x times 1.0 into the fp32 accumulator), the residual then rides the
+            # TMA / tensor-core pipeline at the price of C extra MACs per output
+            if layer.resample == "none":
+                W[p + ".w2r"] = w2.contiguous().to(device)
             w2 = torch.cat([w2, torch.eye(layer.cout, dtype=w2.dtype, device=w2.device)], dim=1)
         W[p + ".w2"], W[p + ".b2"] = w2.contiguous().to(device), f32(b2)
 
@@ -358,10 +371,11 @@ class Plan:
         elif layer.cin != layer.cout:
             out, _ = self._conv(segs2 + [(s_, MODE_1x1) for s_ in srcs], W[p + ".w2"], layer.cout, H, Wd,
                                 ebias=W[p + ".b2"])
-        else:
-            resid = xr if xr is not None else srcs[0]
-            out, _ = self._conv(segs2 + [(resid, MODE_1x1)], W[p + ".w2"], layer.cout, H, Wd, ebias=W[p + ".b2"],
+        elif SKIP_AS_K:
+            out, _ = self._conv(segs2 + [(srcs[0], MODE_1x1)], W[p + ".w2"], layer.cout, H, Wd, ebias=W[p + ".b2"],
                                 algo_flops=2.0 * self.N * H * Wd * layer.cout * 9 * layer.cout)
+        else:
+            out, _ = self._conv(segs2, W[p + ".w2r"], layer.cout, H, Wd, ebias=W[p + ".b2"], residual=srcs[0])
         self.pool.release(aff2)
         self._free(h)
         if xr is not None:
@@ -507,11 +521,17 @@ class Plan:
         st = eng.state
         self._emit(lambda: ops.slerp_h(self.middle_h.t, self.dh_user, self.h2.t, self.h2.stats, st["slerp_t"],
                                        st["use_mask"]), "slerp")
-        # ---- decoders: (h2 -> et_mod) and (h -> et); same weights, same skip tensors
+        # ---- decoders: (h2 -> et_mod) and (h -> et); same weights, same skip tensors.  The second pass allocates from
+        # its own pool: in an edit step the two passes are independent and run CONCURRENTLY on two streams
+        # (run_edit_and_decoder) — a persistent conv kernel leaves SMs idle in its last wave (512 tiles on 148 SMs =
+        # 3.46 rounds), and the other pass's kernel fills them
         self._cur = self.dec_mod_ops
         self._decoder(self.h2, self.et_mod)
         self._cur = self.dec_ops
+        main_pool, self.pool = self.pool, Pool(dev)
         self._decoder(self.middle_h, self.et)
+        self.side_pool, self.pool = self.pool, main_pool
+        self.side_stream = torch.cuda.Stream(device=dev)
         self.mid_f32 = torch.zeros(N, a.mid_ch, h.H, h.W, dtype=torch.float32, device=dev)
         self.delta_f32 = torch.zeros_like(self.mid_f32)
 
@@ -641,6 +661,20 @@ class Plan:
         for f in self.dec_ops:
             f()
 
+    def run_edit_and_decoder(self, explicit=False):
+        """edit step: Δh injection + decoder(h2) on the current stream, decoder(h) concurrently on the side stream
+        (fork / join by events; inside a stream capture this becomes two parallel branches of the graph)"""
+        if not DUAL_STREAM:
+            self.run_edit(explicit)
+            self.run_decoder()
+            return
+        cur = torch.cuda.current_stream()
+        self.side_stream.wait_stream(cur)
+        with torch.cuda.stream(self.side_stream):
+            self.run_decoder()
+        self.run_edit(explicit)
+        cur.wait_stream(self.side_stream)
+
 
 class UNetEngine:
     """Device weights + plans for one UNet."""
@@ -745,11 +779,12 @@ class UNetEngine:
                 if edit:
                     if explicit:
                         P.dh_user.copy_(rec["dh_in"][ei])
-                    P.run_edit(explicit=explicit)
+                    P.run_edit_and_decoder(explicit=explicit)
                     if record_dh:
                         ops.unpack_nchw(P.delta_h.t, rec["delta_h"][ei])
                     ei += 1
-                P.run_decoder()
+                else:
+                    P.run_decoder()
                 z = None
                 if s.stochastic:
                     z = zbuf[zi]
@@ -774,8 +809,9 @@ class UNetEngine:
                 P.emb_all.copy_(emb_table[0])
                 P.run_encoder()
                 if explicit or self.n_delta:
-                    P.run_edit(explicit=explicit)
-                P.run_decoder()
+                    P.run_edit_and_decoder(explicit=explicit)
+                else:
+                    P.run_decoder()
             torch.cuda.current_stream().wait_stream(s_)
             torch.cuda.synchronize(self.device)
             cg = torch.cuda.CUDAGraph()

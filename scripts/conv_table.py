@@ -5,9 +5,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from bench import WORKLOADS, build_model
 ap = argparse.ArgumentParser(); ap.add_argument("--workload", default="ddpm_celeba_b16"); ap.add_argument("--batch", type=int)
 a = ap.parse_args()
-family, key, batch, _ = WORKLOADS[a.workload]; batch = a.batch or batch
-m = build_model(family, key, torch.device("cuda:0"))
-P = m.engine.plan(batch); P.x.normal_(); P.t.fill_(999.0); P.set_coeffs((1.0, 1.0))
+family, key, batch, _, ckpt, _ = WORKLOADS[a.workload]; batch = a.batch or batch
+m, _ = build_model(family, key, torch.device("cuda:0"), ckpt)
+P = m.engine.plan(batch); P.x.normal_(); P.t.fill_(999.0); P.set_coeffs((1.0, 1.0)); P.run_temb()
 seq = P.launches(True)
 prof = P.profile(edit=True, reps=5)
 agg = collections.OrderedDict()

@@ -14,14 +14,15 @@ ap.add_argument("--workload", default="ddpm_celeba_b16")
 ap.add_argument("--batch", type=int, default=None)
 ap.add_argument("--reps", type=int, default=1)
 a = ap.parse_args()
-family, key, batch, _ = WORKLOADS[a.workload]
+family, key, batch, _, ckpt, _ = WORKLOADS[a.workload]
 batch = a.batch or batch
 dev = torch.device("cuda:0")
-m = build_model(family, key, dev)
+m, _ = build_model(family, key, dev, ckpt)
 P = m.engine.plan(batch)
 P.x.normal_()
 P.t.fill_(999.0)
 P.set_coeffs((1.0, 1.0))
+P.run_temb()
 for _ in range(a.reps):
     P.run_encoder()
     P.run_edit()

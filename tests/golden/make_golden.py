@@ -270,7 +270,9 @@ def trajectory_fixture(name, family, cfg, key, B, n_step, chunk=4):
             xo = o_smp.run_trajectory(lambda *a, **k: fwd(sd, *a, **k), x[:1], betas=betas, seq=seq, seq_next=seq_next,
                                       t_edit=500, t_addnoise=200, index=0, hs_coeff=(1.0, 1.0),
                                       learn_sigma=family == "adm", noises={i: v[:1] for i, v in noises.items()})
-            assert torch.equal(xo, xf[:1]), (xo - xf[:1]).abs().max()
+            # bit-equal at equal batch size (checked by mini() / full_trajectory()); here the reference ran a chunk of
+            # `chunk` samples and oneDNN blocks a B=4 conv differently from a B=1 one: ~1e-6 relative
+            assert (xo - xf[:1]).abs().max() <= 2e-5 * xf[:1].abs().max(), (xo - xf[:1]).abs().max()
         outs.append(xf)
         print(f"  {name}: samples {sl.start}..{sl.stop - 1} done ({time.time() - t0:.0f}s)", flush=True)
     xf = torch.cat(outs)
