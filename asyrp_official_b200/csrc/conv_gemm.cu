@@ -180,22 +180,14 @@ __device__ __forceinline__ void transform_fast(uint32_t base, uint32_t vld, uint
 #pragma unroll
   for (int k = 0; k < U; ++k) {
     __half2* h2 = reinterpret_cast<__half2*>(&u[k]);
-    float v[8];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const float2 f = __half22float2(h2[e]);
-      v[2 * e] = fmaf(ca[2 * e], f.x, cb[2 * e]);
-      v[2 * e + 1] = fmaf(ca[2 * e + 1], f.y, cb[2 * e + 1]);
+      float2 f = __half22float2(h2[e]);
+      f.x = fmaf(ca[2 * e], f.x, cb[2 * e]);
+      f.y = fmaf(ca[2 * e + 1], f.y, cb[2 * e + 1]);
+      if (act) { f.x = silu_fast(f.x); f.y = silu_fast(f.y); }
+      h2[e] = __floats2half2_rn(f.x, f.y);
     }
-    if (act == 1) {  // one reciprocal per four activations (the transform is special-function bound)
-      silu4_fast(v[0], v[1], v[2], v[3]);
-      silu4_fast(v[4], v[5], v[6], v[7]);
-    } else if (act == 2) {  // one reciprocal per activation (A/B reference)
-#pragma unroll
-      for (int e = 0; e < 8; ++e) v[e] = silu_fast(v[e]);
-    }
-#pragma unroll
-    for (int e = 0; e < 4; ++e) h2[e] = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
     if (CHK && !((img >> k) & 1u)) u[k] = make_uint4(0u, 0u, 0u, 0u);
   }
 #pragma unroll
@@ -203,12 +195,45 @@ __device__ __forceinline__ void transform_fast(uint32_t base, uint32_t vld, uint
     if (!CHK || ((vld >> k) & 1u)) sts128(base + k * 4096, u[k]);
 }
 
+// Residual values of one 32-pixel chunk (rows row0 .. of the tile, this lane's channel) read through the resample index
+// map: mode 1 nearest-x2 (tile pixel (dy, dx) <- source pixel (dy >> 1, dx >> 1) of the half-resolution tensor; tile
+// origins are even), mode 2 2x2 average pool of the double-resolution tensor in fp32 like F.avg_pool2d.
+// rp: source tensor at the tile's origin and this lane's channel; rrow / cout: elements per source row / pixel.
+template <int TWS>
+__device__ __noinline__ void load_resampled_residual(__half2 (&rv)[16], const __half* rp, int mode, int row0, int rrow,
+                                                     int cout) {
+  constexpr int TW = 1 << TWS;
+  if (mode == 1) {
+    rp += static_cast<size_t>(row0 >> 1) * rrow;
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) {
+      const __half v0 = rp[((i >> TWS) >> 1) * rrow + ((i & (TW - 1)) >> 1) * cout];
+      rv[i >> 1] = __halves2half2(v0, v0);  // pixels i, i+1 share their source pixel (i even)
+    }
+  } else {
+    rp += static_cast<size_t>(row0 * 2) * rrow;
+#pragma unroll 4
+    for (int i = 0; i < 32; i += 2) {
+      float a2[2];
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const __half* q = rp + ((i + k) >> TWS) * 2 * rrow + ((i + k) & (TW - 1)) * 2 * cout;
+        a2[k] = 0.25f * ((__half2float(q[0]) + __half2float(q[cout])) + (__half2float(q[rrow]) + __half2float(q[rrow + cout])));
+      }
+      rv[i >> 1] = __floats2half2_rn(a2[0], a2[1]);
+    }
+  }
+}
+
 // Swapped-operand epilogue of one warp: TMEM lane = output channel c, columns = the tile's pixels (row-major in the
 // TW x (MT*128/TW) tile); this warp drains the 32-pixel column chunks half, half+2, ...  TWS = log2(TW).
-template <int TWS, int MT>
+// RES: the residual is read through a resample index map (ADM up / down blocks); a separate instantiation so that the
+// common one (the hot loop of 55 % of the conv time, instruction-issue bound) carries no extra live registers
+template <int TWS, int MT, bool RES>
 __device__ __forceinline__ void swap_epilogue(const ConvParams& p, uint32_t taddr, int half, size_t obase,
                                               int row_stride, int cout, int lane_off, uint32_t sel, float eb,
-                                              float scale, float rs, size_t rbase, int rrow, float& s1, float& s2) {
+                                              size_t rbase, int rrow, float& s1, float& s2) {
+  const float scale = p.acc_scale, rs = p.res_scale;  // constant-bank operands (device-side scales: generic tile only)
   // obase: element offset of the tile's first pixel at this lane's channel; row_stride / cout: elements between
   // vertically / horizontally adjacent tile pixels in the output (doubled for the sub-pixel phases of an up2 conv)
   constexpr int TW = 1 << TWS;
@@ -223,35 +248,15 @@ __device__ __forceinline__ void swap_epilogue(const ConvParams& p, uint32_t tadd
     const size_t o0 = obase + static_cast<size_t>(cc * kRows) * row_stride;
     __half2 rv[16];
     if (resp != nullptr) {  // all residual loads first: independent of the stores below
-      if (p.res_mode == 0) {
+      if constexpr (!RES) {
         const __half* rp = resp + o0;
 #pragma unroll
         for (int i = 0; i < 32; i += 2)
           rv[i >> 1] = __halves2half2(rp[(i >> TWS) * row_stride + (i & (TW - 1)) * cout],
                                       rp[((i + 1) >> TWS) * row_stride + ((i + 1) & (TW - 1)) * cout]);
-      } else if (p.res_mode == 1) {
-        // nearest-x2: tile pixel (dy, dx) reads source pixel (dy >> 1, dx >> 1) of the half-resolution tensor
-        // (tile origins are even); rrow = elements per source row, cout here = p.Cout (no up2 output scatter)
-        const __half* rp = resp + rbase + static_cast<size_t>((cc * kRows) >> 1) * rrow;
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const __half v0 = rp[((i >> TWS) >> 1) * rrow + ((i & (TW - 1)) >> 1) * cout];
-          rv[i >> 1] = __halves2half2(v0, v0);  // pixels i, i+1 share their source pixel (i even)
-        }
       } else {
-        // 2x2 average pool of the double-resolution tensor, fp32 like F.avg_pool2d
-        const __half* rp = resp + rbase + static_cast<size_t>(cc * kRows * 2) * rrow;
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float a2[2];
-#pragma unroll
-          for (int k = 0; k < 2; ++k) {
-            const __half* q = rp + ((i + k) >> TWS) * 2 * rrow + ((i + k) & (TW - 1)) * 2 * cout;
-            a2[k] = 0.25f * ((__half2float(q[0]) + __half2float(q[cout])) +
-                             (__half2float(q[rrow]) + __half2float(q[rrow + cout])));
-          }
-          rv[i >> 1] = __floats2half2_rn(a2[0], a2[1]);
-        }
+        // ADM up / down blocks only: kept out of line so that the common path's register allocation is untouched
+        load_resampled_residual<TWS>(rv, resp + rbase, p.res_mode, cc * kRows, rrow, cout);
       }
     }
     tmem_ld_wait();
@@ -768,7 +773,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
         // tile.  The swapped tile is only selected when it lies fully inside the image (conv_config), so there are
         // no bounds predicates here: this epilogue is instruction-issue bound (it set a ~9 us floor per tile).
         const int c = nt * 128 + q * 32 + lane;
-        const float eb = eb_swap * acc_scale;
+        const float eb = eb_swap * p.acc_scale;
         const bool odd = (lane & 1) != 0;
         // lanes (2j, 2j+1) hold adjacent channels: the even lane stores pixel i, the odd lane pixel i+1, each as one
         // half2 (channel pair) -> a warp store covers two pixels x 64 B
@@ -776,20 +781,26 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
         const int pix_stride = p.Cout * ps, row_stride = OW * pix_stride;
         const int lane_off = odd ? pix_stride - 1 : 0;
         const size_t obase = ((static_cast<size_t>(tn) * OH + ty * THT * ps + pa) * OW + tx * p.TW * ps + pb) * p.Cout + c;
-        // residual source geometry for res_mode 1 (half resolution) / 2 (double resolution)
-        const int rW = p.res_mode == 1 ? (p.W >> 1) : (p.W << 1), rH = p.res_mode == 1 ? (p.H >> 1) : (p.H << 1);
-        const int rrow = rW * p.Cout;
-        const size_t rbase =
-            p.res_mode == 1
-                ? ((static_cast<size_t>(tn) * rH + ((ty * THT) >> 1)) * rW + ((tx * p.TW) >> 1)) * p.Cout + c
-                : ((static_cast<size_t>(tn) * rH + ty * THT * 2) * rW + tx * p.TW * 2) * p.Cout + c;
         float s1 = 0.f, s2 = 0.f;
-        if (p.TW == 8)
-          swap_epilogue<3, MT>(p, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kAccCols, half, obase,
-                               row_stride, pix_stride, lane_off, sel, eb, acc_scale, res_scale, rbase, rrow, s1, s2);
-        else
-          swap_epilogue<4, MT>(p, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kAccCols, half, obase,
-                               row_stride, pix_stride, lane_off, sel, eb, acc_scale, res_scale, rbase, rrow, s1, s2);
+        const uint32_t tq = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kAccCols;
+        if (p.res_mode == 0) {
+          if (p.TW == 8)
+            swap_epilogue<3, MT, false>(p, tq, half, obase, row_stride, pix_stride, lane_off, sel, eb, 0, 0, s1, s2);
+          else
+            swap_epilogue<4, MT, false>(p, tq, half, obase, row_stride, pix_stride, lane_off, sel, eb, 0, 0, s1, s2);
+        } else {
+          // residual source geometry for res_mode 1 (half resolution) / 2 (double resolution)
+          const int rW = p.res_mode == 1 ? (p.W >> 1) : (p.W << 1), rH = p.res_mode == 1 ? (p.H >> 1) : (p.H << 1);
+          const int rrow = rW * p.Cout;
+          const size_t rbase =
+              p.res_mode == 1
+                  ? ((static_cast<size_t>(tn) * rH + ((ty * THT) >> 1)) * rW + ((tx * p.TW) >> 1)) * p.Cout + c
+                  : ((static_cast<size_t>(tn) * rH + ty * THT * 2) * rW + tx * p.TW * 2) * p.Cout + c;
+          if (p.TW == 8)
+            swap_epilogue<3, MT, true>(p, tq, half, obase, row_stride, pix_stride, lane_off, sel, eb, rbase, rrow, s1, s2);
+          else
+            swap_epilogue<4, MT, true>(p, tq, half, obase, row_stride, pix_stride, lane_off, sel, eb, rbase, rrow, s1, s2);
+        }
         if (p.stats != nullptr) {
           // channel pair = lanes (2j, 2j+1); each (tile, half) owns one slot: nothing to reduce across warps
           s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
@@ -1344,6 +1355,8 @@ ASYRP_API int asyrp_conv_create(const AsyrpConvDesc* d, void** out_op) {
   p.res_scale = d->res_scale;
   p.acc_scale = d->acc_scale;
   p.scales = d->scales;
+  ASYRP_REQUIRE(d->scales == nullptr || !(op->BN == 128 && op->MT == 2),
+                "asyrp_conv_create: device-side scales are not supported by the swapped-operand tile");
   p.res_mode = d->residual != nullptr ? d->res_mode : 0;
   ASYRP_REQUIRE(p.res_mode >= 0 && p.res_mode <= 2, "asyrp_conv_create: res_mode %d", d->res_mode);
   ASYRP_REQUIRE(p.res_mode == 0 || (!p.up2 && p.out_heads == 1 && !d->out_f32 && d->out_planar == nullptr &&

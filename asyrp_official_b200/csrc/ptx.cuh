@@ -312,24 +312,4 @@ __device__ __forceinline__ float silu_fast(float x) {
   return x * r;
 }
 
-// SiLU of four values with ONE reciprocal: sigma_i = 1 / d_i, d_i = 1 + 2^(-y_i log2 e);  1/d_0 = d_1 d_2 d_3 / (d_0 d_1 d_2
-// d_3) etc.  The operand transform of the conv kernel is bound by the special-function unit (16 lanes/clk/SM): this is
-// 5 MUFU per 4 elements instead of 8.  The exponent is clamped at 2^30 so that the product of four denominators stays
-// finite (y < -20.8 gives |silu| < 2e-8 either way, below fp16's smallest subnormal).  Relative error ~2^-21.
-__device__ __forceinline__ void silu4_fast(float& y0, float& y1, float& y2, float& y3) {
-  float e0, e1, e2, e3, r;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fminf(y0 * -1.4426950408889634f, 30.f)));
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fminf(y1 * -1.4426950408889634f, 30.f)));
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e2) : "f"(fminf(y2 * -1.4426950408889634f, 30.f)));
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e3) : "f"(fminf(y3 * -1.4426950408889634f, 30.f)));
-  const float d0 = 1.0f + e0, d1 = 1.0f + e1, d2 = 1.0f + e2, d3 = 1.0f + e3;
-  const float p01 = d0 * d1, p23 = d2 * d3;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(p01 * p23));
-  const float r01 = r * p23, r23 = r * p01;
-  y0 *= r01 * d1;
-  y1 *= r01 * d0;
-  y2 *= r23 * d3;
-  y3 *= r23 * d2;
-}
-
 }  // namespace asyrp

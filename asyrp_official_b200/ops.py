@@ -11,10 +11,7 @@ import torch
 from . import _lib
 from ._lib import AsyrpConvDesc, check
 
-import os
-
 MODE_1x1, MODE_3x3, MODE_3x3_S2 = 0, 1, 2
-_SILU_PER_ELEMENT = os.environ.get("ASYRP_SILU_PER_ELEMENT", "0") == "1"  # A/B: one reciprocal per activation
 RESAMPLE_NONE, RESAMPLE_AVGPOOL2, RESAMPLE_UP2 = 0, 1, 2
 
 
@@ -124,7 +121,7 @@ class ConvOp:
                 assert aff.dtype == torch.float32 and aff.is_contiguous() and aff.shape[-1] == 2
                 d.seg[i].affine = aff.data_ptr() + aff_off * 2 * 4
                 d.seg[i].affine_stride = aff.shape[1] * 2
-                d.seg[i].act = int(act) * (2 if (act and _SILU_PER_ELEMENT) else 1)
+                d.seg[i].act = int(act)
             ktot += (1 if mode == MODE_1x1 else (4 if up2 else 9)) * src.shape[-1]
         assert weight.dtype == torch.float16 and weight.stride(-1) == 1 and weight.shape[-1] == ktot, \
             (weight.shape, weight.stride(), ktot)
