@@ -1165,6 +1165,15 @@ ASYRP_API int asyrp_conv_stats_tiles(int H, int W, int Cout, int has_3x3) {
   return NB == 1 ? tiles : tiles * 4;
 }
 
+// tile configuration of a conv with this output geometry: BN * 16 + MT (e.g. 128 * 16 + 2 = the swapped-operand
+// 128-channel x 256-pixel tile).  Lets the caller route work that the swapped tile's epilogue handles badly (a
+// residual read through a resample index map: scattered 2-byte loads per lane) to another formulation.
+ASYRP_API int asyrp_conv_tile_config(int H, int W, int Cout, int has_3x3) {
+  int bn, mt;
+  conv_config(H, W, Cout, has_3x3 && conv_halo_ok(H, W), &bn, &mt);
+  return bn * 16 + mt;
+}
+
 // statistics slots per sample written by an up2 conv over an H x W SOURCE image (output 2H x 2W)
 ASYRP_API int asyrp_conv_stats_tiles_up2(int H, int W, int Cout) {
   int TW, TH, NB, bn, mt;

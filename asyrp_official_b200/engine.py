@@ -339,6 +339,13 @@ class Plan:
             # materialised (a quarter of the input's size).
             src = srcs[0]
             res_mode = 1 if mode == RESAMPLE_UP2 else 2
+            Ho = src.H * 2 if mode == RESAMPLE_UP2 else src.H // 2
+            if ops.conv_tile_config(Ho, Ho * src.W // src.H, layer.cout, True) == (128, 2):
+                # swapped-operand tile: its epilogue owns one channel per lane, a resampled residual is 32 scattered
+                # 2-byte loads per chunk (measured 260 vs 121 us at 256^2) -> materialise x_upd(x) and add it as
+                # identity K columns like every other skip
+                res_mode = 0
+                xr = self._apply(srcs, None, 0, mode)
             up_fused = mode == RESAMPLE_UP2 and src.H >= 16 and ops.conv_stats_tiles_up2(src.H, src.W, layer.cout) > 0
             if up_fused:
                 H, Wd = 2 * src.H, 2 * src.W
@@ -371,8 +378,9 @@ class Plan:
         elif layer.cin != layer.cout:
             out, _ = self._conv(segs2 + [(s_, MODE_1x1) for s_ in srcs], W[p + ".w2"], layer.cout, H, Wd,
                                 ebias=W[p + ".b2"])
-        elif SKIP_AS_K:
-            out, _ = self._conv(segs2 + [(srcs[0], MODE_1x1)], W[p + ".w2"], layer.cout, H, Wd, ebias=W[p + ".b2"],
+        elif SKIP_AS_K or xr is not None:
+            out, _ = self._conv(segs2 + [(xr if xr is not None else srcs[0], MODE_1x1)], W[p + ".w2"], layer.cout, H, Wd,
+                                ebias=W[p + ".b2"],
                                 algo_flops=2.0 * self.N * H * Wd * layer.cout * 9 * layer.cout)
         else:
             out, _ = self._conv(segs2, W[p + ".w2r"], layer.cout, H, Wd, ebias=W[p + ".b2"], residual=srcs[0])

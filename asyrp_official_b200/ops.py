@@ -65,6 +65,12 @@ def conv_stats_tiles(H, W, C, has_3x3):
     return _lib.load().asyrp_conv_stats_tiles(H, W, C, int(has_3x3))
 
 
+def conv_tile_config(H, W, C, has_3x3):
+    """(BN, MT) of the tile the library uses for this output geometry; (128, 2) is the swapped-operand tile"""
+    v = _lib.load().asyrp_conv_tile_config(H, W, C, int(has_3x3))
+    return v // 16, v % 16
+
+
 def conv_stats_tiles_up2(H, W, C):
     """slots per sample of the statistics an up2 conv over an H x W source writes (0: geometry unsupported)"""
     return _lib.load().asyrp_conv_stats_tiles_up2(H, W, C)

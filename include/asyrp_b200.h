@@ -113,6 +113,9 @@ typedef struct AsyrpConvDesc {
 /* number of tile slots of the stats buffer of a conv with this output geometry; has_3x3: the conv has an
  * ASYRP_CONV_3x3 segment (selects the 8x16 halo tile geometry when H%16==0 and W%8==0) */
 int asyrp_conv_stats_tiles(int H, int W, int Cout, int has_3x3);
+/* tile configuration the library picks for this output geometry: BN * 16 + MT (BN output channels x MT * 128 pixels per
+ * CTA tile; 128 * 16 + 2 is the swapped-operand tile) */
+int asyrp_conv_tile_config(int H, int W, int Cout, int has_3x3);
 /* the same for an up2 conv over an H x W source image (0 if the geometry is unsupported) */
 int asyrp_conv_stats_tiles_up2(int H, int W, int Cout);
 /* CTA pairs: convs whose tile is 128 pixels x 256 channels run as clusters of two CTAs (the two SMs of a TPC) that share
