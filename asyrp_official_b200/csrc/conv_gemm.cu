@@ -462,7 +462,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
                 mbar_wait_suspend(&emptyB[sb], pb ^ 1);
                 if constexpr (CTA2) {
                   // this CTA's half of the weight rows; the bytes of both halves are counted on the leader's barrier
-                  const uint32_t bar = mapa_shared(smem_u32(&fullB[sb]), 0u);
+                  // the leader's copy of fullB[sb]: shared-window addresses carry the CTA's rank within the pair in bit
+                  // 24; clearing it is plain ALU work on a warp-uniform value (a `mapa` result lives in a vector
+                  // register and would put the TMA instruction into a vote / R2UR waterfall loop)
+                  const uint32_t bar = smem_u32(&fullB[sb]) & 0xFEFFFFFFu;
                   if (elect_one()) {
                     if (cta_rank == 0) mbar_arrive_expect_tx(&fullB[sb], 2 * kBStage);
                     tma_load_4d_2cta(sB + sb * kBStage, &p.tmB, bar, sg.kbase + tap * sg.C + ch * 64,

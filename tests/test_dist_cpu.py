@@ -34,11 +34,23 @@ def _worker(rank, world, port, q):
     mine = [b for b in range(7) if b % r.world == r.rank]
     gathered = [None] * world
     dist.all_gather_object(gathered, mine)
-    q.put((rank, same, m._version > v0, gathered))
+    # cache files (precomputed/*.pth, diffusion_latent.py:974-982,1082,1167): rank 0 writes through a temp file + rename,
+    # the other ranks wait at a barrier and load — nobody reads a half-written file, nobody duplicates the inversion
+    from asyrp_official_b200.diffusion_latent import _atomic_save
+    path = os.path.join(os.environ["ASYRP_TEST_TMP"], "pairs.pth")
+    value = None
+    if rank == 0:
+        value = [[torch.full((1, 3, 4, 4), float(i)), torch.zeros(1, 3, 4, 4), torch.ones(1, 3, 4, 4) * i] for i in range(3)]
+        _atomic_save(value, path)
+    got = r._sync_cache(path, value)
+    cache_ok = len(got) == 3 and all(torch.equal(t[0], torch.full((1, 3, 4, 4), float(i))) for i, t in enumerate(got)) \
+        and not [f for f in os.listdir(os.environ["ASYRP_TEST_TMP"]) if ".tmp." in f]
+    q.put((rank, same and cache_ok, m._version > v0, gathered))
     dist.destroy_process_group()
 
 
-def test_broadcast_and_sharding_world2():
+def test_broadcast_and_sharding_world2(tmp_path):
+    os.environ["ASYRP_TEST_TMP"] = str(tmp_path)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29600 + os.getpid() % 300
@@ -50,6 +62,6 @@ def test_broadcast_and_sharding_world2():
         p.join(60)
         assert p.exitcode == 0
     for rank, same, bumped, gathered in res:
-        assert same, f"rank {rank}: weights differ from rank 0 after broadcast"
+        assert same, f"rank {rank}: weights differ from rank 0 after broadcast, or the rank-0 cache was not received"
         assert bumped
         assert sorted(gathered[0] + gathered[1]) == list(range(7)) and not set(gathered[0]) & set(gathered[1])
