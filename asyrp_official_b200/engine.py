@@ -24,6 +24,9 @@ from .ops import MODE_1x1, MODE_3x3, MODE_3x3_S2, RESAMPLE_AVGPOOL2, RESAMPLE_NO
 
 # ASYRP_DUAL_STREAM=0: run the two decoder passes of an edit step one after the other (A/B measurements)
 DUAL_STREAM = os.environ.get("ASYRP_DUAL_STREAM", "1") != "0"
+# layers narrower than this keep a pointwise GroupNorm-apply launch instead of the in-kernel operand transform
+# (ASYRP_FUSE_MIN_H=8 fuses the 8x8 layers too: 28 launches fewer per edit evaluation)
+FUSE_MIN_H = int(os.environ.get("ASYRP_FUSE_MIN_H", "16"))
 # ResBlock identity skips x + h ride conv2's K loop as an identity weight block (C extra MACs per output, exact: fp16 x
 # times 1.0 into the fp32 accumulator).  ASYRP_SKIP_AS_K=0 reads x in the epilogue instead.  A/B on one B200 (round 2,
 # ABAB order): 35.57 / 35.51 img/s with the K columns vs 34.39 / 34.30 with the epilogue read — the scattered fp16
@@ -306,7 +309,7 @@ class Plan:
         Layers smaller than 16x16 keep the pointwise kernel: their K loop is a chain of short stages, and the in-kernel
         transform (one stage at a time) would sit on the critical path; the tensors are ~1 MB."""
         segs, off = [], 0
-        small = srcs[0].H < 16
+        small = srcs[0].H < FUSE_MIN_H
         for s_ in srcs:
             if small:
                 a_ = self._apply([s_], aff, act, affine_offset=off)
