@@ -23,3 +23,6 @@ print("--- individual launches of 128->128 @256x256 single-segment fused convs")
 for L, (kind, ms, fl, nb) in zip(seq, prof):
     if kind == "conv" and getattr(L, "desc", "") in ("3x3*:128 -> 128 @256x256", "3x3*:128 -> 128 @128x128", "3x3:128 -> 128 @256x256"):
         print(L.desc, f"{ms*1000:.1f} us", f"{fl/ms/1e9:.0f} TF/s", "has_res" if getattr(L, "has_res", None) else "")
+print("--- launch order (kind | desc | algorithmic GFLOP), for joining with an ncu launch list")
+for L in seq:
+    print(f"LAUNCH|{L.kind}|{getattr(L, 'desc', '')}|{L.flops / 1e9:.3f}")
