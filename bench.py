@@ -49,7 +49,8 @@ WORKLOADS = {
     "ddpm_celeba_b16": ("ddpm", "celeba", 16, 40, "smiling_LC_CelebA_HQ_t999_ninv40_ngen40_0.pth",
                         "ddpm_celeba_smiling_traj40_b16.npz"),
     "iddpm_afhq_b8": ("adm", "afhq", 8, 40, "dog_happy_LC_dog_t999_ninv40_ngen40_0.pth", "adm_afhq_happy_traj40.npz"),
-    "ddpm_church_b32": ("ddpm", "church", 32, 40, "church_gothic_LC_church_outdoor_t999_ninv40_ngen40_0.pth", None),
+    "ddpm_church_b32": ("ddpm", "church", 32, 40, "church_gothic_LC_church_outdoor_t999_ninv40_ngen40_0.pth",
+                        "ddpm_church_gothic_traj40.npz"),
     "adm_imagenet_b4": ("adm", "imagenet", 4, 50, None, "adm_imagenet_traj50.npz"),
 }
 # algorithmic GFLOP per image per UNet pass (2*MAC), SURVEY.md §8(d): encoder, decoder, delta block

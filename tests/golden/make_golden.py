@@ -16,6 +16,7 @@ Fixtures (npz, fp32):
                                     ({"0": layer_0.state_dict()}, the part diffusion_latent.py:674-676 loads)
   ddpm_celeba_smiling_traj40_b16.npz   BASELINE configs[1] in full: B=16, 40-step edit, 'smiling' DeltaBlock
   adm_afhq_happy_traj40.npz            configs[2] at B=1: iDDPM-AFHQ, 'dog_happy' DeltaBlock, 40 steps
+  ddpm_church_gothic_traj40.npz        configs[3] at B=1: DDPM LSUN-Church (same UNet as CelebA), 'church_gothic' block
   adm_imagenet_traj50.npz              configs[4] at B=1: ADM-ImageNet, seeded DeltaBlock, 50 steps
                                     (trajectory fixtures: stride-4 subsample of x_0, |x_0| max, seeds, sequence)
 """
@@ -298,7 +299,7 @@ if __name__ == "__main__":
         elif t == "imagenet":
             trajectory_fixture("adm_imagenet_traj50", "adm", o_adm.IMAGENET_HP, "imagenet", 1, 50)
         elif t == "church":
-            shipped_delta_block("church")
+            trajectory_fixture("ddpm_church_gothic_traj40", "ddpm", o_ddpm.CELEBA_CFG, "church", 1, 40)
         else:
             raise SystemExit(f"unknown trajectory fixture {t}")
     if args.skip_mini:
