@@ -14,7 +14,10 @@ c_void_p, c_int, c_float = C.c_void_p, C.c_int, C.c_float
 
 class AsyrpConvSeg(C.Structure):
     _fields_ = [("src", c_void_p), ("C", c_int), ("mode", c_int), ("affine", c_void_p), ("affine_stride", c_int),
-                ("act", c_int), ("ld", c_int)]
+                ("act", c_int), ("ld", c_int),
+                ("gn_sums_a", c_void_p), ("gn_Ca", c_int), ("gn_sums_b", c_void_p), ("gn_Cb", c_int),
+                ("gn_gamma", c_void_p), ("gn_beta", c_void_p), ("gn_scale_shift", c_void_p), ("gn_ss_stride", c_int),
+                ("gn_eps", c_float), ("gn_hw", c_int), ("gn_off", c_int)]
 
 
 class AsyrpConvDesc(C.Structure):
@@ -38,6 +41,7 @@ class AsyrpConvDesc(C.Structure):
         ("up2", c_int),
         ("scales", c_void_p),
         ("res_mode", c_int),
+        ("sums_out", c_void_p),
     ]
 
 

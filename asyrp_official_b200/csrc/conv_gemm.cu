@@ -47,7 +47,20 @@ struct ConvSegDev {
   const float* affine;  // [N][aff_stride] floats: (a, b) pairs of this segment's channels, or nullptr
   int aff_stride;
   int act;              // 1: SiLU after the affine
+  // In-kernel GroupNorm finalise (replaces the affine table and the gn_finalize launch that fills it): the transform
+  // threads compute (a, b) of their 8 channels from per-(sample, channel pair) sums that the PRODUCERS' epilogues
+  // accumulated with 64-bit integer atomics (fixed point, kStatScale): integer addition commutes, so the statistics —
+  // and everything downstream — stay bit-reproducible whatever order the tiles finish in.
+  const long long* gn_sums[2];  // [N][C_i/2][2] (sum, sum of squares) of the two sources of the (virtual) concat
+  int gn_C[2];                  // their channel counts (gn_C[1] == 0: single source)
+  const float* gn_gamma;        // [C_total] GroupNorm weight / bias on the concatenated axis; nullptr = mode off
+  const float* gn_beta;
+  const float* gn_ss;           // ADM: (scale | shift) rows [N][gn_ss_stride] (improved_ddpm/unet.py:290-294) or nullptr
+  int gn_ss_stride;
+  float gn_eps, gn_inv_count;   // 1 / (H*W * channels per group)
+  int gn_off;                   // first channel of this segment on the concatenated axis
 };
+static constexpr float kStatScale = 262144.0f;  // 2^18: resolution 3.8e-6 per tile sum, range +-3.5e13
 
 struct ConvParams {
   CUtensorMap tmA[kMaxSeg];
@@ -84,6 +97,7 @@ struct ConvParams {
   float* out_planar;       // optional fp32 planar [N][planar_c][H][W] holding output channels [0, planar_c)
   int planar_c;
   float* stats;            // [N][tiles_y*tiles_x][Cout/2][2] partial (sum, sumsq) or nullptr
+  long long* sums_out;     // [N][Cout/2][2] fixed-point (sum, sumsq) accumulated with integer atomics, or nullptr
   int b_batched;           // weights have a per-sample batch dimension (attention GEMMs)
   // multi-head attention GEMMs: the batch index ns of a tile is (sample, head).  a_heads > 1: the activation map has
   // a head dimension (64-channel slices of one tensor); b_heads likewise for the per-sample weights; out_heads > 1:
@@ -193,6 +207,68 @@ __device__ __forceinline__ void transform_fast(uint32_t base, uint32_t vld, uint
 #pragma unroll
   for (int k = 0; k < U; ++k)
     if (!CHK || ((vld >> k) & 1u)) sts128(base + k * 4096, u[k]);
+}
+
+// (a, b) of 8 consecutive channels [c0, c0+8) of segment `sg` for sample n:  GroupNorm(32 groups over the concatenated
+// channel axis, eps) [* (1 + scale) + shift] as y = a*x + b.  Same arithmetic as gn_finalize_kernel (fp64 mean / var),
+// evaluated by every transform thread for its own channels once per (tile, 64-channel chunk): a group's sums are
+// 1..24 16-byte loads that all threads of the CTA share through L1.  The 8 channels touch at most 4 groups (2 channels
+// per group at C = 64).  Everything is statically indexed: ca / cb must stay in registers for the transform loop.
+__device__ __forceinline__ void gn_group_stats(const ConvSegDev& sg, int n, int g, int cpg, double inv, float& mean,
+                                               float& rstd) {
+  long long s1 = 0, s2 = 0;
+  const int pa = sg.gn_C[0] >> 1, pb = sg.gn_C[1] >> 1;
+  const int p_lo = (g * cpg) >> 1, p_hi = p_lo + (cpg >> 1);
+#pragma unroll 1
+  for (int pi = p_lo; pi < p_hi; ++pi) {
+    const long long* q = pi < pa ? sg.gn_sums[0] + (static_cast<size_t>(n) * pa + pi) * 2
+                                 : sg.gn_sums[1] + (static_cast<size_t>(n) * pb + (pi - pa)) * 2;
+    const longlong2 v = *reinterpret_cast<const longlong2*>(q);
+    s1 += v.x;
+    s2 += v.y;
+  }
+  const double m = static_cast<double>(s1) * inv;
+  double var = static_cast<double>(s2) * inv - m * m;
+  if (var < 0.0) var = 0.0;
+  rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(sg.gn_eps)));
+  mean = static_cast<float>(m);
+}
+__device__ __forceinline__ void gn_affine8(const ConvSegDev& sg, int n, int c0, float (&ca)[8], float (&cb)[8]) {
+  const int C = sg.gn_C[0] + sg.gn_C[1], cpg = C >> 5;
+  const int cg0 = sg.gn_off + c0;
+  const double inv = static_cast<double>(sg.gn_inv_count) * (1.0 / static_cast<double>(kStatScale));
+  const int g0 = cg0 / cpg, ng = (cg0 + 7) / cpg - g0 + 1;  // 1, 2 or 4 groups
+  float gm[4] = {0.f, 0.f, 0.f, 0.f}, gr[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (k < ng) gn_group_stats(sg, n, g0 + k, cpg, inv, gm[k], gr[k]);
+  const float4* gp = reinterpret_cast<const float4*>(sg.gn_gamma + cg0);
+  const float4* bp = reinterpret_cast<const float4*>(sg.gn_beta + cg0);
+  const float4 g_lo = gp[0], g_hi = gp[1], b_lo = bp[0], b_hi = bp[1];
+  const float gam[8] = {g_lo.x, g_lo.y, g_lo.z, g_lo.w, g_hi.x, g_hi.y, g_hi.z, g_hi.w};
+  const float bet[8] = {b_lo.x, b_lo.y, b_lo.z, b_lo.w, b_hi.x, b_hi.y, b_hi.z, b_hi.w};
+  int bound = (g0 + 1) * cpg - cg0;  // channels [0, bound) of the 8 belong to group g0, and so on
+  int k = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    if (i >= bound) { ++k; bound += cpg; }
+    const float mean = k == 0 ? gm[0] : (k == 1 ? gm[1] : (k == 2 ? gm[2] : gm[3]));
+    const float rstd = k == 0 ? gr[0] : (k == 1 ? gr[1] : (k == 2 ? gr[2] : gr[3]));
+    float a = gam[i] * rstd;
+    float b = bet[i] - mean * a;
+    if (sg.gn_ss != nullptr) {
+      const float* ssp = sg.gn_ss + static_cast<size_t>(n) * sg.gn_ss_stride + cg0 + i;
+      const float sc = 1.0f + ssp[0];
+      const float sh = ssp[C];
+      a = a * sc;
+      b = b * sc + sh;
+    }
+    ca[i] = a;
+    cb[i] = b;
+  }
+}
+__device__ __forceinline__ void stat_atomic_add(long long* dst, float v) {
+  atomicAdd(reinterpret_cast<unsigned long long*>(dst), static_cast<unsigned long long>(__float2ll_rn(v * kStatScale)));
 }
 
 // Residual values of one 32-pixel chunk (rows row0 .. of the tile, this lane's channel) read through the resample index
@@ -631,11 +707,13 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
                 const float4 t4 = ap[k];
                 ca[2 * k] = t4.x; cb[2 * k] = t4.y; ca[2 * k + 1] = t4.z; cb[2 * k + 1] = t4.w;
               }
+            } else if (sg.gn_gamma != nullptr) {  // GroupNorm finalise in place of the table (NB == 1 by construction)
+              gn_affine8(sg, n0 < p.N ? n0 : 0, ch * 64 + jl * 8, ca, cb);
             }
             for (int cp = 0; cp < ncopies; ++cp) {
               const int slot = lt ? p.a_stages + sl : sa;
               mbar_wait_suspend(&fullA[slot], lt ? plt : pa);
-              if (sg.affine != nullptr) {
+              if (sg.affine != nullptr || sg.gn_gamma != nullptr) {
                 uint8_t* stage = lt ? sL + sl * p.l_stage_bytes : sA + sa * p.a_stage_bytes;
                 const int xoff = sg.mode == 3 ? -1 : (sg.mode == 1 ? cp - 1 : 0);
                 // whole tile inside the image (always true for halo tiles; 1x1 stages of ragged layers fall back)
@@ -808,10 +886,16 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
           // channel pair = lanes (2j, 2j+1); each (tile, half) owns one slot: nothing to reduce across warps
           s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
           s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
-          if ((lane & 1) == 0)
+          if ((lane & 1) == 0) {
             *reinterpret_cast<float2*>(p.stats + ((static_cast<size_t>(tn) * tiles_per_sample * 2 +
                                                     tile_in_sample * 2 + half) * (p.Cout / 2) + (c >> 1)) * 2) =
                 make_float2(s1, s2);
+            if (p.sums_out != nullptr) {
+              long long* q = p.sums_out + (static_cast<size_t>(tn) * (p.Cout / 2) + (c >> 1)) * 2;
+              stat_atomic_add(q, s1);
+              stat_atomic_add(q + 1, s2);
+            }
+          }
         }
       } else if constexpr (BN == 16) {
         // narrow-N tile of conv_out (3 / 6 real output channels, fp32 planar store): one 16-column load per sub-tile,
@@ -1007,6 +1091,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
           float* g = p.stats + ((static_cast<size_t>(tn) * tiles_per_sample + tile_in_sample) * (p.Cout / 2) +
                                 (nt * BN + cc * 32) / 2 + (j & 15)) * 2 + (j >> 4);
           *g = tot;
+          if (p.sums_out != nullptr)
+            stat_atomic_add(p.sums_out + (static_cast<size_t>(tn) * (p.Cout / 2) + (nt * BN + cc * 32) / 2 + (j & 15)) * 2 +
+                                (j >> 4), tot);
         }
       }
     }
@@ -1058,6 +1145,18 @@ struct AsyrpConvSeg {
   int affine_stride;
   int act;              // 1: SiLU
   int ld;               // elements between consecutive pixels of `src` (0: C) — channel slices of a wider tensor
+  // in-kernel GroupNorm finalise (alternative to `affine`): see ConvSegDev
+  const long long* gn_sums_a;
+  int gn_Ca;
+  const long long* gn_sums_b;
+  int gn_Cb;
+  const float* gn_gamma;
+  const float* gn_beta;
+  const float* gn_scale_shift;
+  int gn_ss_stride;
+  float gn_eps;
+  int gn_hw;
+  int gn_off;
 };
 
 struct AsyrpConvDesc {
@@ -1084,6 +1183,7 @@ struct AsyrpConvDesc {
   int up2;  // 1: sub-pixel evaluation of conv3x3(nearest-x2 upsample(src)): see ConvParams::up2
   const float* scales;  // optional DEVICE pointer to (acc_scale, res_scale); overrides the two fields above at run time
   int res_mode;         // 0: residual has the output geometry; 1: [N][H/2][W/2][Cout], nearest-x2; 2: [N][2H][2W][Cout], avg-pool 2x2
+  long long* sums_out;  // optional [N][Cout/2][2] int64: (sum, sumsq) * 2^18 of the output, accumulated atomically
 };
 
 static void conv_tile_shape(int H, int W, int halo, int* TW, int* TH, int* NB);
@@ -1256,6 +1356,25 @@ ASYRP_API int asyrp_conv_create(const AsyrpConvDesc* d, void** out_op) {
     p.seg[s].aff_stride = sg.affine_stride;
     p.seg[s].act = sg.act;
     ASYRP_REQUIRE(!(sg.affine != nullptr && sg.mode == 2), "asyrp_conv_create: no fused affine on stride-2 segments");
+    if (sg.gn_gamma != nullptr) {
+      ASYRP_REQUIRE(sg.affine == nullptr && sg.gn_sums_a != nullptr && sg.gn_beta != nullptr && sg.gn_Ca > 0 &&
+                        (sg.gn_Ca + sg.gn_Cb) % 64 == 0 && sg.gn_Ca % 2 == 0 && (sg.gn_Cb == 0 || sg.gn_sums_b != nullptr) &&
+                        sg.gn_hw > 0 && sg.mode != 2 && p.NB == 1,
+                    "asyrp_conv_create: in-kernel GroupNorm needs sums, gamma / beta, a stride-1 segment and tiles "
+                    "inside one sample");
+      p.seg[s].gn_sums[0] = sg.gn_sums_a;
+      p.seg[s].gn_sums[1] = sg.gn_sums_b;
+      p.seg[s].gn_C[0] = sg.gn_Ca;
+      p.seg[s].gn_C[1] = sg.gn_Cb;
+      p.seg[s].gn_gamma = sg.gn_gamma;
+      p.seg[s].gn_beta = sg.gn_beta;
+      p.seg[s].gn_ss = sg.gn_scale_shift;
+      p.seg[s].gn_ss_stride = sg.gn_ss_stride;
+      p.seg[s].gn_eps = sg.gn_eps;
+      p.seg[s].gn_inv_count = 1.0f / (static_cast<float>(sg.gn_hw) * static_cast<float>((sg.gn_Ca + sg.gn_Cb) / 32));
+      p.seg[s].gn_off = sg.gn_off;
+      p.any_transform = 1;
+    }
     if (sg.affine != nullptr) p.any_transform = 1;
     ktot += (sg.mode == 0 ? 1 : (p.up2 ? 4 : 9)) * sg.C;
     any3 = any3 || sg.mode == 1;
@@ -1376,6 +1495,9 @@ ASYRP_API int asyrp_conv_create(const AsyrpConvDesc* d, void** out_op) {
                 "asyrp_conv_create: resampled residual needs a plain NHWC fp16 output (even H, W for nearest-x2)");
   p.out = static_cast<__half*>(d->out);
   p.stats = d->stats;
+  p.sums_out = d->sums_out;
+  ASYRP_REQUIRE(d->sums_out == nullptr || (d->stats != nullptr && p.NB == 1 && op->BN >= 32),
+                "asyrp_conv_create: sums_out needs stats and tiles inside one sample");
   op->smem_bytes = 1024 + static_cast<size_t>(p.a_stages) * p.a_stage_bytes +
                    static_cast<size_t>(p.l_stages) * p.l_stage_bytes + static_cast<size_t>(p.b_stages) * b_stage +
                    (3 * (p.a_stages + p.l_stages) + 2 * p.b_stages + 4) * 8 + 16 + 2 * 4 * op->BN * 4;

@@ -27,6 +27,10 @@ DUAL_STREAM = os.environ.get("ASYRP_DUAL_STREAM", "1") != "0"
 # layers narrower than this keep a pointwise GroupNorm-apply launch instead of the in-kernel operand transform
 # (ASYRP_FUSE_MIN_H=8 fuses the 8x8 layers too: 28 launches fewer per edit evaluation)
 FUSE_MIN_H = int(os.environ.get("ASYRP_FUSE_MIN_H", "16"))
+# GroupNorm finalised inside the consuming conv kernel from integer-atomic per-sample sums the producers' epilogues
+# accumulate (no gn_finalize launch, no affine table) for every layer of at least 16x16; ASYRP_GN_FOLD=0: one
+# asyrp_gn_finalize launch per GroupNorm as in round 1
+GN_FOLD = os.environ.get("ASYRP_GN_FOLD", "1") != "0"
 # ResBlock identity skips x + h ride conv2's K loop as an identity weight block (C extra MACs per output, exact: fp16 x
 # times 1.0 into the fp32 accumulator).  ASYRP_SKIP_AS_K=0 reads x in the epilogue instead.  A/B on one B200 (round 2,
 # ABAB order): 35.57 / 35.51 img/s with the K columns vs 34.39 / 34.30 with the epilogue read — the scattered fp16
@@ -35,11 +39,12 @@ SKIP_AS_K = os.environ.get("ASYRP_SKIP_AS_K", "1") != "0"
 
 
 class Act:
-    """NHWC fp16 activation + the partial GroupNorm sums its producer wrote"""
-    __slots__ = ("t", "stats")
+    """NHWC fp16 activation + the partial GroupNorm sums its producer wrote (per-tile fp32 slots, and — for layers whose
+    consumers finalise the GroupNorm in-kernel — per-sample int64 accumulators)"""
+    __slots__ = ("t", "stats", "sums")
 
-    def __init__(self, t, stats=None):
-        self.t, self.stats = t, stats
+    def __init__(self, t, stats=None, sums=None):
+        self.t, self.stats, self.sums = t, stats, sums
 
     @property
     def C(self):
@@ -63,6 +68,37 @@ class Launch:
 
     def __call__(self):
         self.fn()
+
+
+class GN:
+    """One GroupNorm over the channel concat of `srcs`, in whichever form its consumers need: `spec()` for convs that
+    finalise it in-kernel, `table()` (emits the asyrp_gn_finalize launch, once) for the pointwise apply kernel."""
+
+    def __init__(self, plan, srcs, gamma, beta, scale_shift=None, ss_stride=0):
+        self.plan, self.srcs, self.gamma, self.beta, self.ss, self.ss_stride = plan, srcs, gamma, beta, scale_shift, ss_stride
+        self._table = None
+
+    def spec(self):
+        if not GN_FOLD or any(s_.sums is None for s_ in self.srcs):
+            return None
+        a = self.srcs[0]
+        return ops.GNSpec([s_.sums for s_ in self.srcs], [s_.C for s_ in self.srcs], self.gamma, self.beta,
+                          self.plan.eng.arch.gn_eps, a.H * a.W, self.ss, self.ss_stride)
+
+    def operand(self):
+        """what a fused conv segment takes: the in-kernel spec when available, else the affine table"""
+        sp = self.spec()
+        return sp if sp is not None else self.table()
+
+    def table(self):
+        if self._table is None:
+            self._table = self.plan._gn_table(self.srcs, self.gamma, self.beta, self.ss, self.ss_stride)
+        return self._table
+
+    def release(self):
+        if self._table is not None:
+            self.plan.pool.release(self._table)
+            self._table = None
 
 
 class Pool:
@@ -234,6 +270,10 @@ class Plan:
         # DeltaBlock coefficients (acc_scale, res_scale) of the h2 = c0*h + sum_i c_{i+1}*delta_h_i epilogues live in
         # device memory: one captured graph serves every hs_coeff tuple
         self.coef = torch.ones(max(eng.n_delta, 1), 2, dtype=torch.float32, device=dev)
+        # int64 (sum, sum of squares) accumulators of every >= 16x16 conv output, one arena zeroed by ONE memset at the
+        # start of an evaluation (a buffer is never reused: two producers must not add into the same sums)
+        self.sums_arena = torch.zeros(max(1 << 20, N * 98304), dtype=torch.int64, device=dev) if GN_FOLD else None
+        self.sums_used = 0
         self._temps = []     # materialised operands to release after the next conv launch is recorded
         self._cur = self.enc_ops
         self._build()
@@ -245,11 +285,16 @@ class Plan:
 
     def _act(self, H, W, C, stats=False, has_3x3=False, tiles=None):
         t = self.pool.alloc((self.N, H, W, C), torch.float16)
-        st = None
+        st, sums = None, None
         if stats:
             tiles = tiles if tiles is not None else ops.conv_stats_tiles(H, W, C, has_3x3)
             st = self.pool.alloc((self.N, tiles, C // 2, 2), torch.float32)
-        return Act(t, st)
+            if GN_FOLD and H >= 16 and W >= 16:  # tiles lie inside one sample: the epilogue can add per-sample sums
+                n = self.N * C
+                assert self.sums_used + n <= self.sums_arena.numel(), "sums arena exhausted"
+                sums = self.sums_arena[self.sums_used:self.sums_used + n].view(self.N, C // 2, 2)
+                self.sums_used += n
+        return Act(t, st, sums)
 
     def _free(self, act):
         self.pool.release(act.t)
@@ -257,6 +302,9 @@ class Plan:
             self.pool.release(act.stats)
 
     def _gn(self, srcs, gamma, beta, scale_shift=None, ss_stride=0):
+        return GN(self, srcs, gamma, beta, scale_shift, ss_stride)
+
+    def _gn_table(self, srcs, gamma, beta, scale_shift=None, ss_stride=0):
         N = self.N
         C = sum(s.C for s in srcs)
         aff = self.pool.alloc((N, C, 2), torch.float32)
@@ -290,7 +338,8 @@ class Plan:
         op = ops.ConvOp([(sg[0].t,) + sg[1:] for sg in segs], weight, out=out.t if out else None, ebias=ebias,
                         ebias_stride=ebias_stride, residual=residual.t if residual is not None else None,
                         res_scale=res_scale, acc_scale=acc_scale, stats=out.stats if out else None,
-                        out_planar=planar, out_shape=(self.N, H, W, Cout), up2=up2, scales=scales, res_mode=res_mode)
+                        out_planar=planar, out_shape=(self.N, H, W, Cout), up2=up2, scales=scales, res_mode=res_mode,
+                        sums_out=out.sums if out else None)
         ktot = weight.shape[-1]
         flops = algo_flops if algo_flops is not None else 2.0 * self.N * H * W * Cout * ktot
         nbytes = 2.0 * (sum(sg[0].t.numel() for sg in segs) + weight.numel() + self.N * H * W * Cout
@@ -312,11 +361,11 @@ class Plan:
         small = srcs[0].H < FUSE_MIN_H
         for s_ in srcs:
             if small:
-                a_ = self._apply([s_], aff, act, affine_offset=off)
+                a_ = self._apply([s_], aff.table(), act, affine_offset=off)
                 self._temps.append(a_)
                 segs.append((a_, mode))
             else:
-                segs.append((s_, mode, aff, off, act))
+                segs.append((s_, mode, aff.operand(), off, act))
             off += s_.C
         return segs
 
@@ -352,9 +401,9 @@ class Plan:
             up_fused = mode == RESAMPLE_UP2 and src.H >= 16 and ops.conv_stats_tiles_up2(src.H, src.W, layer.cout) > 0
             if up_fused:
                 H, Wd = 2 * src.H, 2 * src.W
-                segs1 = [(src, MODE_3x3, aff1, 0, 1)]
+                segs1 = [(src, MODE_3x3, aff1.operand(), 0, 1)]
             else:
-                a1 = self._apply(srcs, aff1, 1, mode)
+                a1 = self._apply(srcs, aff1.table(), 1, mode)
                 segs1, H, Wd = [(a1, MODE_3x3)], a1.H, a1.W
         else:
             segs1, H, Wd = self._fused(srcs, MODE_3x3, aff1, 1), srcs[0].H, srcs[0].W
@@ -371,7 +420,7 @@ class Plan:
             # GN(h)*(1+scale)+shift, [scale | shift] = Linear(SiLU(emb))  (unet.py:287-294)
             aff2 = self._gn([h], W[p + ".g2"], W[p + ".be2"], self.emb_all[:, eoff:eoff + 2 * layer.cout],
                             eng.emb_total)
-        self.pool.release(aff1)
+        aff1.release()
         if a1 is not None:
             self._free(a1)
         segs2 = self._fused([h], MODE_3x3, aff2, 1)
@@ -387,7 +436,7 @@ class Plan:
                                 algo_flops=2.0 * self.N * H * Wd * layer.cout * 9 * layer.cout)
         else:
             out, _ = self._conv(segs2, W[p + ".w2r"], layer.cout, H, Wd, ebias=W[p + ".b2"], residual=srcs[0])
-        self.pool.release(aff2)
+        aff2.release()
         self._free(h)
         if xr is not None:
             self._free(xr)
@@ -402,7 +451,7 @@ class Plan:
         aff = self._gn([x], W[p + ".g"], W[p + ".be"])
         qkv, _ = self._conv(self._fused([x], MODE_1x1, aff, 0), W[p + ".wqkv"], 3 * C, x.H, x.W, ebias=W[p + ".bqkv"],
                             stats=False)
-        self.pool.release(aff)
+        aff.release()
         self._drop_temps()
         att = self._act(x.H, x.W, C, stats=False)
         N, T = self.N, x.H * x.W
@@ -502,6 +551,8 @@ class Plan:
                    nbytes=4.0 * W["emb_cat.w"].numel())
         # ---- encoder
         self._cur = self.enc_ops
+        if GN_FOLD:  # zero every int64 statistics accumulator of the evaluation (encoder and both decoder passes) at once
+            self._emit(lambda: self.sums_arena[:self.sums_used].zero_(), "memset")
         xin = self._act(S, S, 64, stats=False)
         self._emit(lambda: ops.pack_input(self.x, xin.t), "pack_input", nbytes=4.0 * self.x.numel() + 2.0 * xin.t.numel())
         first_ch = a.enc[1][0].cin
@@ -565,7 +616,7 @@ class Plan:
         self._emit(lambda: (op_nt if st["ignore_timestep"] else op_t).launch(), "conv",
                    2.0 * self.N * h.H * h.W * C * C)
         if aff1 is not None:
-            self.pool.release(aff1)
+            aff1.release()
         aff = self._gn([d1], W[p + ".g2"], W[p + ".be2"])
         seg2 = self._fused([d1], MODE_1x1, aff, 1)
         if last:  # API-visible delta_h = output of the last DeltaBlock
@@ -574,7 +625,7 @@ class Plan:
         # h2 = c_{i+1} * (conv2(a2) + b2) + (c0*h | 1*h2_prev), with GroupNorm partial sums for the decoder
         h2, op = self._conv(seg2, W[p + ".w2"], C, h.H, h.W, ebias=W[p + ".b2"], residual=h2_prev,
                             scales=self.coef[i])
-        self.pool.release(aff)
+        aff.release()
         self._free(d1)
         self._drop_temps()
         if h2_prev is not h:
@@ -591,7 +642,7 @@ class Plan:
         aff = self._gn([h], W["norm_out.g"], W["norm_out.be"])
         self._conv(self._fused([h], MODE_3x3, aff, 1), W["conv_out.w"], 16, h.H, h.W, ebias=W["conv_out.b"],
                    stats=False, planar=out_planar, algo_flops=2.0 * self.N * h.H * h.W * a.out_ch * 9 * h.C)
-        self.pool.release(aff)
+        aff.release()
         self._free(h)
         self._drop_temps()
 

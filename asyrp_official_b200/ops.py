@@ -82,6 +82,28 @@ def new_stats(N, H, W, C, device, has_3x3):
     return torch.zeros(N, conv_stats_tiles(H, W, C, has_3x3), C // 2, 2, dtype=torch.float32, device=device)
 
 
+STAT_SCALE = 262144.0  # 2^18: fixed-point scale of the int64 (sum, sum of squares) accumulators (csrc kStatScale)
+
+
+def new_sums(N, C, device):
+    """[N][C/2][2] int64 accumulators a conv epilogue adds its output statistics to (zero them before the producer runs)"""
+    return torch.zeros(N, C // 2, 2, dtype=torch.int64, device=device)
+
+
+class GNSpec:
+    """A GroupNorm(32 groups) that the CONSUMING conv finalises inside its kernel (AsyrpConvSeg.gn_*) instead of reading
+    an affine table written by asyrp_gn_finalize: `sums` are the int64 accumulators (ConvOp(sums_out=...)) of the one
+    or two producers of the (virtually concatenated) input, `C` their channel counts."""
+    __slots__ = ("sums", "C", "gamma", "beta", "eps", "hw", "ss", "ss_stride")
+
+    def __init__(self, sums, C, gamma, beta, eps, hw, ss=None, ss_stride=0):
+        self.sums, self.C, self.gamma, self.beta, self.eps, self.hw = list(sums), list(C), gamma, beta, float(eps), int(hw)
+        self.ss, self.ss_stride = ss, int(ss_stride)
+        for t, c in zip(self.sums, self.C):
+            assert t.dtype == torch.int64 and t.is_contiguous() and t.shape[1:] == (c // 2, 2), (t.shape, c)
+        assert gamma.dtype == torch.float32 and gamma.numel() == sum(self.C) == beta.numel()
+
+
 class ConvOp:
     """One implicit-GEMM convolution launch (asyrp_conv_create / asyrp_conv_launch).
 
@@ -93,12 +115,13 @@ class ConvOp:
 
     def __init__(self, segs, weight, out=None, ebias=None, ebias_stride=0, residual=None, res_scale=1.0,
                  acc_scale=1.0, stats=None, out_planar=None, out_shape=None, weight_batched=False, a_heads=1,
-                 b_heads=1, out_heads=1, up2=False, scales=None, res_mode=0):
+                 b_heads=1, out_heads=1, up2=False, scales=None, res_mode=0, sums_out=None):
         lib = _lib.load()
         segs = [tuple(sg) + (None, 0, 0) * (len(sg) == 2) for sg in segs]
         srcs = [sg[0] for sg in segs]
         affs = [sg[2] for sg in segs]
-        _need_cuda(*srcs, *affs, weight, out, ebias, residual, stats, out_planar)
+        _need_cuda(*srcs, *[a for a in affs if not isinstance(a, GNSpec)], weight, out, ebias, residual, stats,
+                   out_planar, sums_out)
         if out is not None:
             N, H, W, Cout = out.shape
             if out_heads > 1:  # out [n][H][W][heads*Cout] receives batch entries (n, head)
@@ -123,7 +146,16 @@ class ConvOp:
             d.seg[i].C = src.shape[-1]
             d.seg[i].mode = mode
             d.seg[i].ld = ld
-            if aff is not None:
+            if isinstance(aff, GNSpec):  # GroupNorm finalised in the kernel; aff_off = first channel on the concat axis
+                d.seg[i].gn_sums_a, d.seg[i].gn_Ca = aff.sums[0].data_ptr(), aff.C[0]
+                if len(aff.sums) > 1:
+                    d.seg[i].gn_sums_b, d.seg[i].gn_Cb = aff.sums[1].data_ptr(), aff.C[1]
+                d.seg[i].gn_gamma, d.seg[i].gn_beta = aff.gamma.data_ptr(), aff.beta.data_ptr()
+                if aff.ss is not None:
+                    d.seg[i].gn_scale_shift, d.seg[i].gn_ss_stride = aff.ss.data_ptr(), aff.ss_stride
+                d.seg[i].gn_eps, d.seg[i].gn_hw, d.seg[i].gn_off = aff.eps, aff.hw, aff_off
+                d.seg[i].act = int(act)
+            elif aff is not None:
                 assert aff.dtype == torch.float32 and aff.is_contiguous() and aff.shape[-1] == 2
                 d.seg[i].affine = aff.data_ptr() + aff_off * 2 * 4
                 d.seg[i].affine_stride = aff.shape[1] * 2
@@ -148,11 +180,14 @@ class ConvOp:
             d.scales = scales.data_ptr()
         d.out = out.data_ptr() if out is not None else None
         d.stats = stats.data_ptr() if stats is not None else None
+        if sums_out is not None:
+            assert sums_out.dtype == torch.int64 and sums_out.is_contiguous() and stats is not None
+            d.sums_out = sums_out.data_ptr()
         if out_planar is not None:
             assert out_planar.dtype == torch.float32
             d.out_planar = out_planar.data_ptr()
             d.planar_c = out_planar.shape[1]
-        self._keep = (srcs, affs, weight, out, ebias, residual, stats, out_planar, scales)
+        self._keep = (srcs, affs, weight, out, ebias, residual, stats, out_planar, scales, sums_out)
         h = C.c_void_p()
         check(lib.asyrp_conv_create(C.byref(d), C.byref(h)), "asyrp_conv_create")
         self._h = h

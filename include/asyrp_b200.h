@@ -68,6 +68,24 @@ typedef struct AsyrpConvSeg {
   int act;         /* 1: SiLU after the affine */
   int ld;          /* elements between consecutive pixels of src (0: C): lets a segment be a channel slice of a wider
                       tensor, e.g. q = qkv[..., 0:C] */
+  /* Alternative to `affine`: GroupNorm finalised INSIDE the kernel (no asyrp_gn_finalize launch, no affine table).
+   * gn_sums_a / gn_sums_b: the `sums_out` buffers of the conv(s) that produced the (one or two, virtually concatenated)
+   * source tensors of the GroupNorm — [N][C_i/2][2] int64, (sum, sum of squares) * 2^18 per channel pair, accumulated by
+   * their epilogues with integer atomics (deterministic) and zeroed by the caller before those convs run; gn_gamma /
+   * gn_beta: [Ca+Cb] GroupNorm weight / bias; gn_scale_shift: optional ADM (scale | shift) rows, row n at
+   * + n*gn_ss_stride; gn_eps; gn_hw = H*W of the normalised tensor; gn_off: first channel of this segment on the
+   * concatenated axis.  Needs tiles inside one sample (H*W >= 128). */
+  const long long* gn_sums_a;
+  int gn_Ca;
+  const long long* gn_sums_b;
+  int gn_Cb;
+  const float* gn_gamma;
+  const float* gn_beta;
+  const float* gn_scale_shift;
+  int gn_ss_stride;
+  float gn_eps;
+  int gn_hw;
+  int gn_off;
 } AsyrpConvSeg;
 
 typedef struct AsyrpConvDesc {
@@ -108,6 +126,9 @@ typedef struct AsyrpConvDesc {
    * [N][2H][2W][Cout], read through a 2x2 average pool — the skip branch x_upd(x) of the ADM ResBlock(up / down)
    * (improved_ddpm/unet.py:279-284,297), so that the resampled copy of x is never materialised */
   int res_mode;
+  /* optional [N][Cout/2][2] int64 accumulators of (sum, sum of squares) * 2^18 of the output, for a consumer's in-kernel
+   * GroupNorm (AsyrpConvSeg.gn_*); requires `stats` */
+  long long* sums_out;
 } AsyrpConvDesc;
 
 /* number of tile slots of the stats buffer of a conv with this output geometry; has_3x3: the conv has an

@@ -598,3 +598,74 @@ def test_subpixel_upconv_with_fused_groupnorm_silu(cuda_device, C, H):
     op.launch()
     torch.cuda.synchronize()
     _check(_from_nhwc(out), ref, 3e-3, "fused up2 conv")
+
+
+@pytest.mark.parametrize("C1,C2,H,mode,ss", [(128, 0, 32, "3x3", False), (128, 64, 32, "3x3", False), (64, 0, 16, "1x1", False),
+                                             (256, 128, 16, "3x3", True), (256, 0, 64, "3x3", True), (512, 256, 16, "1x1", False)])
+def test_groupnorm_finalised_inside_the_consumer_conv(cuda_device, C1, C2, H, mode, ss):
+    """AsyrpConvSeg.gn_*: the producers' epilogues add (sum, sum of squares) per (sample, channel pair) into int64
+    accumulators (integer atomics: deterministic); the consuming conv computes GroupNorm(32) [*(1+scale)+shift] + SiLU of its
+    operand from them — no asyrp_gn_finalize launch, no affine table.  Reference: torch GroupNorm over the concatenated
+    producers' outputs (statistics on the fp32 pre-rounding values, normalisation of the fp16-stored tensor)."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(61)
+    N, W, Cout = 3, H, 128
+    C = C1 + C2
+    srcs, sums, refs = [], [], []
+    for Cs in [c for c in (C1, C2) if c]:
+        xin = _rand((N, 64, H, W), g)
+        w = _rand((Cs, 64, 1, 1), g, 0.3)
+        b = _rand((Cs,), g)
+        out = torch.empty(N, H, W, Cs, dtype=torch.float16, device=cuda_device)
+        st = ops.new_stats(N, H, W, Cs, cuda_device, False)
+        sm = ops.new_sums(N, Cs, cuda_device)
+        op = ops.ConvOp([(_nhwc_half(xin, cuda_device), ops.MODE_1x1)], ops.pack_conv_weight(w).to(cuda_device), out=out,
+                        ebias=b.to(cuda_device), stats=st, sums_out=sm)
+        op.launch()
+        srcs.append(out)
+        sums.append(sm)
+        refs.append(F.conv2d(_h(xin), _h(w)) + b.double()[None, :, None, None])
+    torch.cuda.synchronize()
+    # the accumulators equal the per-tile slots' totals (fixed point, 2^18)
+    xstat = torch.cat(refs, 1)
+    for sm, r in zip(sums, refs):
+        got = sm.double().cpu() / ops.STAT_SCALE
+        want = _stats_ref(r)
+        assert (got - want).abs().max().item() <= 2e-3 * want.abs().max().item() + 1e-3
+    gamma, beta = _rand((C,), g) * 0.3 + 1.0, _rand((C,), g) * 0.3
+    ssv = _rand((N, 2 * C + 5), g, 0.3)[:, 3:3 + 2 * C] if ss else None  # a slice of a wider row, as the engine passes it
+    eps = 1e-5
+    xg = xstat.reshape(N, 32, -1)
+    mean, var = xg.mean(-1), xg.var(-1, unbiased=False)
+    cpg = C // 32
+    mean_c = mean.repeat_interleave(cpg, 1)[:, :, None, None]
+    rstd_c = (1.0 / torch.sqrt(var + eps)).repeat_interleave(cpg, 1)[:, :, None, None]
+    xcat = torch.cat([_from_nhwc(s).double() for s in srcs], 1)
+    y = (xcat - mean_c) * rstd_c * gamma.double()[None, :, None, None] + beta.double()[None, :, None, None]
+    if ss:
+        y = y * (1 + ssv[:, :C].double()[:, :, None, None]) + ssv[:, C:].double()[:, :, None, None]
+    y = _h((y * torch.sigmoid(y)).float())
+    k = 3 if mode == "3x3" else 1
+    w2 = _rand((Cout, C, k, k), g, 1.0 / math.sqrt(k * k * C))
+    ref = F.conv2d(y, _h(w2), padding=k // 2)
+    ssd = None
+    if ss:
+        wide = torch.zeros(N, 2 * C + 5)
+        wide[:, 3:3 + 2 * C] = ssv
+        ssd = wide.to(cuda_device)[:, 3:3 + 2 * C]
+    spec = ops.GNSpec(sums, [c for c in (C1, C2) if c], gamma.to(cuda_device), beta.to(cuda_device), eps, H * W,
+                      ssd, 2 * C + 5 if ss else 0)
+    m = ops.MODE_3x3 if mode == "3x3" else ops.MODE_1x1
+    segs, off, wparts = [], 0, []
+    for x in srcs:
+        segs.append((x, m, spec, off, 1))
+        wparts.append(ops.pack_conv_weight(w2[:, off:off + x.shape[-1]]))
+        off += x.shape[-1]
+    out = torch.empty(N, H, W, Cout, dtype=torch.float16, device=cuda_device)
+    op = ops.ConvOp(segs, torch.cat(wparts, 1).contiguous().to(cuda_device), out=out)
+    op.launch()
+    a = out.clone()
+    op.launch()
+    torch.cuda.synchronize()
+    assert torch.equal(a, out)
+    _check(_from_nhwc(out), ref, 3e-3, f"in-kernel GroupNorm {mode} C={C1}+{C2}")
