@@ -106,6 +106,7 @@ struct ConvParams {
   int out_ld;              // elements between consecutive output pixels (Cout * out_heads)
   int out_f32;             // `out` is fp32 (attention logits keep fp32 precision for the softmax)
   int any_transform;       // some segment has an affine: the MMA warp then waits on readyA instead of fullA
+  int any_gn;              // some segment finalises its GroupNorm in the kernel (per-tile group statistics in smem)
   // up2: this conv is "3x3 conv of the nearest-x2 upsampled input" (Upsample.conv, ddpm/diffusion.py:77-87) evaluated
   // on the SOURCE image as four sub-pixel phases: output pixel (2i+a, 2j+b) only ever sees the 2x2 source
   // neighbourhood rows {i-1+a, i+a} x cols {j-1+b, j+b}, with the 3x3 taps that fall on the same source pixel summed
@@ -233,15 +234,14 @@ __device__ __forceinline__ void gn_group_stats(const ConvSegDev& sg, int n, int 
   rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(sg.gn_eps)));
   mean = static_cast<float>(m);
 }
-__device__ __forceinline__ void gn_affine8(const ConvSegDev& sg, int n, int c0, float (&ca)[8], float (&cb)[8]) {
+// (a, b) of this thread's 8 channels from the tile's group statistics `gs` ([32] (mean, rstd) in shared memory, written
+// once per tile by 32 lanes, see the transform role): everything statically indexed, ca / cb stay in registers.
+__device__ __forceinline__ void gn_affine8(const ConvSegDev& sg, const float2* gs, int n, int c0, float (&ca)[8],
+                                           float (&cb)[8]) {
   const int C = sg.gn_C[0] + sg.gn_C[1], cpg = C >> 5;
   const int cg0 = sg.gn_off + c0;
-  const double inv = static_cast<double>(sg.gn_inv_count) * (1.0 / static_cast<double>(kStatScale));
-  const int g0 = cg0 / cpg, ng = (cg0 + 7) / cpg - g0 + 1;  // 1, 2 or 4 groups
-  float gm[4] = {0.f, 0.f, 0.f, 0.f}, gr[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-  for (int k = 0; k < 4; ++k)
-    if (k < ng) gn_group_stats(sg, n, g0 + k, cpg, inv, gm[k], gr[k]);
+  const int g0 = cg0 / cpg;  // the 8 channels touch at most 4 groups (2 channels per group at C = 64)
+  const float2 s0 = gs[g0], s1 = gs[min(g0 + 1, 31)], s2 = gs[min(g0 + 2, 31)], s3 = gs[min(g0 + 3, 31)];
   const float4* gp = reinterpret_cast<const float4*>(sg.gn_gamma + cg0);
   const float4* bp = reinterpret_cast<const float4*>(sg.gn_beta + cg0);
   const float4 g_lo = gp[0], g_hi = gp[1], b_lo = bp[0], b_hi = bp[1];
@@ -252,10 +252,9 @@ __device__ __forceinline__ void gn_affine8(const ConvSegDev& sg, int n, int c0, 
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     if (i >= bound) { ++k; bound += cpg; }
-    const float mean = k == 0 ? gm[0] : (k == 1 ? gm[1] : (k == 2 ? gm[2] : gm[3]));
-    const float rstd = k == 0 ? gr[0] : (k == 1 ? gr[1] : (k == 2 ? gr[2] : gr[3]));
-    float a = gam[i] * rstd;
-    float b = bet[i] - mean * a;
+    const float2 st = k == 0 ? s0 : (k == 1 ? s1 : (k == 2 ? s2 : s3));
+    float a = gam[i] * st.y;
+    float b = bet[i] - st.x * a;
     if (sg.gn_ss != nullptr) {
       const float* ssp = sg.gn_ss + static_cast<size_t>(n) * sg.gn_ss_stride + cg0 + i;
       const float sc = 1.0f + ssp[0];
@@ -411,6 +410,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
   float* s_stats = reinterpret_cast<float*>(tmem_slot + 4);  // [2][4][BN/32][32]
+  float2* s_gstat = reinterpret_cast<float2*>(s_stats + 2 * 4 * BN);  // [2][kMaxSeg][32] (mean, rstd), see gn_affine8
   const int THT = MT * p.TH;  // rows of the CTA tile
 
   if (threadIdx.x == 0) {
@@ -683,10 +683,32 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
       }
       int sa = 0, sl = 0;
       uint32_t pa = 0, plt = 0;
-      for (int w = worker0; w < n_work; w += n_workers) {
+      // In-kernel GroupNorm: lane g of transform warp s computes (mean, rstd) of group g of segment s for the sample of a
+      // tile, ONE tile ahead (the buffer of tile i+1 is written while tile i is transformed; the named barrier at the
+      // top of tile i+1 publishes it).  fp64 like gn_finalize_kernel; 32 x nseg threads per tile, not every thread.
+      auto group_stats = [&](int w_next, int buf) {
+        const int s = tt >> 5;
+        if (s < p.nseg && p.seg[s].gn_gamma != nullptr) {
+          const ConvSegDev& sg = p.seg[s];
+          const TileCoord tcn = tile_coord(p, own_tile(w_next));
+          const int n = tcn.tn < p.N ? tcn.tn : 0;  // NB == 1
+          const int cpg = (sg.gn_C[0] + sg.gn_C[1]) >> 5;
+          float m, r;
+          gn_group_stats(sg, n, tt & 31, cpg,
+                         static_cast<double>(sg.gn_inv_count) * (1.0 / static_cast<double>(kStatScale)), m, r);
+          s_gstat[(buf * kMaxSeg + s) * 32 + (tt & 31)] = make_float2(m, r);
+        }
+      };
+      if (p.any_gn && worker0 < n_work) group_stats(worker0, 0);
+      int git = 0;
+      for (int w = worker0; w < n_work; w += n_workers, ++git) {
         const int tile = own_tile(w);
         const TileCoord tc = tile_coord(p, tile);
         const int x0 = tc.tx * p.TW, y0 = tc.ty * THT, n0 = tc.tn * p.NB;
+        if (p.any_gn) {
+          named_bar_sync(2, kNumTransformWarps * 32);
+          if (w + n_workers < n_work) group_stats(w + n_workers, (git + 1) & 1);
+        }
         for (int e = 0; e < p.n_sched; ++e) {
           const int s = p.sched[e] >> 6, ch = p.sched[e] & 63;
           const ConvSegDev sg = p.seg[s];
@@ -708,7 +730,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
                 ca[2 * k] = t4.x; cb[2 * k] = t4.y; ca[2 * k + 1] = t4.z; cb[2 * k + 1] = t4.w;
               }
             } else if (sg.gn_gamma != nullptr) {  // GroupNorm finalise in place of the table (NB == 1 by construction)
-              gn_affine8(sg, n0 < p.N ? n0 : 0, ch * 64 + jl * 8, ca, cb);
+              gn_affine8(sg, s_gstat + ((git & 1) * kMaxSeg + s) * 32, n0 < p.N ? n0 : 0, ch * 64 + jl * 8, ca, cb);
             }
             for (int cp = 0; cp < ncopies; ++cp) {
               const int slot = lt ? p.a_stages + sl : sa;
@@ -1374,6 +1396,7 @@ ASYRP_API int asyrp_conv_create(const AsyrpConvDesc* d, void** out_op) {
       p.seg[s].gn_inv_count = 1.0f / (static_cast<float>(sg.gn_hw) * static_cast<float>((sg.gn_Ca + sg.gn_Cb) / 32));
       p.seg[s].gn_off = sg.gn_off;
       p.any_transform = 1;
+      p.any_gn = 1;
     }
     if (sg.affine != nullptr) p.any_transform = 1;
     ktot += (sg.mode == 0 ? 1 : (p.up2 ? 4 : 9)) * sg.C;
@@ -1458,7 +1481,8 @@ ASYRP_API int asyrp_conv_create(const AsyrpConvDesc* d, void** out_op) {
   // operand rings: everything the 227 KB of shared memory leaves after barriers and the statistics scratch.
   // Activations: 3-4 stages; weights: as deep as fits (<= 16 stages) — small-N tiles issue an MMA group every ~100
   // cycles, so the weight prefetch must run many K steps ahead of the ~1 us TMA latency.
-  const uint32_t ring_budget = 227 * 1024 - 1024 /*alignment*/ - 1024 /*barriers*/ - 2 * 4 * op->BN * 4 /*stats*/;
+  const uint32_t ring_budget = 227 * 1024 - 1024 /*alignment*/ - 1024 /*barriers*/ - 2 * 4 * op->BN * 4 /*stats*/ -
+                               2048 /*per-tile GroupNorm group statistics: 2 x 3 x 32 float2*/;
   bool has_light = false;
   for (int s = 0; s < d->nseg; ++s) has_light = has_light || d->seg[s].mode == 0;
   p.l_stages = 0;
@@ -1500,7 +1524,8 @@ ASYRP_API int asyrp_conv_create(const AsyrpConvDesc* d, void** out_op) {
                 "asyrp_conv_create: sums_out needs stats and tiles inside one sample");
   op->smem_bytes = 1024 + static_cast<size_t>(p.a_stages) * p.a_stage_bytes +
                    static_cast<size_t>(p.l_stages) * p.l_stage_bytes + static_cast<size_t>(p.b_stages) * b_stage +
-                   (3 * (p.a_stages + p.l_stages) + 2 * p.b_stages + 4) * 8 + 16 + 2 * 4 * op->BN * 4;
+                   (3 * (p.a_stages + p.l_stages) + 2 * p.b_stages + 4) * 8 + 16 + 2 * 4 * op->BN * 4 +
+                   2 * kMaxSeg * 32 * sizeof(float2);
   ASYRP_REQUIRE(op->smem_bytes <= 227 * 1024, "asyrp_conv_create: smem %zu too large", op->smem_bytes);
   const int sms = sm_count();
   if (sms <= 0) { delete op; return ASYRP_ERR_NO_DEVICE; }
