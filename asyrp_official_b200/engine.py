@@ -27,10 +27,14 @@ DUAL_STREAM = os.environ.get("ASYRP_DUAL_STREAM", "1") != "0"
 # layers narrower than this keep a pointwise GroupNorm-apply launch instead of the in-kernel operand transform
 # (ASYRP_FUSE_MIN_H=8 fuses the 8x8 layers too: 28 launches fewer per edit evaluation)
 FUSE_MIN_H = int(os.environ.get("ASYRP_FUSE_MIN_H", "16"))
-# GroupNorm finalised inside the consuming conv kernel from integer-atomic per-sample sums the producers' epilogues
-# accumulate (no gn_finalize launch, no affine table) for every layer of at least 16x16; ASYRP_GN_FOLD=0: one
-# asyrp_gn_finalize launch per GroupNorm as in round 1
-GN_FOLD = os.environ.get("ASYRP_GN_FOLD", "1") != "0"
+# ASYRP_GN_FOLD=1: GroupNorm finalised inside the consuming conv kernel from integer-atomic per-sample sums the
+# producers' epilogues accumulate (no gn_finalize launch, no affine table) for every layer of at least 16x16: 226 instead
+# of 315 launches per edit evaluation, non-conv time 1.04 -> 0.68 ms — but the conv kernels pay more than that back
+# (per-tile group statistics on the transform warps' critical path, 64-bit atomics in every epilogue): measured
+# 34.2 -> 32.0 img/s (DDPM b16), 35.8 -> 33.7 (AFHQ b8), 5.45 -> 5.17 (ImageNet b4).  Off by default; the path is
+# complete and covered by tests (test_groupnorm_finalised_inside_the_consumer_conv, and the whole GPU suite passes
+# with it on).
+GN_FOLD = os.environ.get("ASYRP_GN_FOLD", "0") == "1"
 # ResBlock identity skips x + h ride conv2's K loop as an identity weight block (C extra MACs per output, exact: fp16 x
 # times 1.0 into the fp32 accumulator).  ASYRP_SKIP_AS_K=0 reads x in the epilogue instead.  A/B on one B200 (round 2,
 # ABAB order): 35.57 / 35.51 img/s with the K columns vs 34.39 / 34.30 with the epilogue read — the scattered fp16
