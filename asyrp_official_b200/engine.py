@@ -34,7 +34,8 @@ FUSE_MIN_H = int(os.environ.get("ASYRP_FUSE_MIN_H", "16"))
 # 34.2 -> 32.0 img/s (DDPM b16), 35.8 -> 33.7 (AFHQ b8), 5.45 -> 5.17 (ImageNet b4).  Off by default; the path is
 # complete and covered by tests (test_groupnorm_finalised_inside_the_consumer_conv, and the whole GPU suite passes
 # with it on).
-GN_FOLD = os.environ.get("ASYRP_GN_FOLD", "0") == "1"
+GN_FOLD = os.environ.get("ASYRP_GN_FOLD", "0") in ("1", "2")
+GN_FOLD_PRODUCERS_ONLY = os.environ.get("ASYRP_GN_FOLD", "0") == "2"  # diagnostic: atomics on, consumers use tables
 # ResBlock identity skips x + h ride conv2's K loop as an identity weight block (C extra MACs per output, exact: fp16 x
 # times 1.0 into the fp32 accumulator).  ASYRP_SKIP_AS_K=0 reads x in the epilogue instead.  A/B on one B200 (round 2,
 # ABAB order): 35.57 / 35.51 img/s with the K columns vs 34.39 / 34.30 with the epilogue read — the scattered fp16
@@ -83,7 +84,7 @@ class GN:
         self._table = None
 
     def spec(self):
-        if not GN_FOLD or any(s_.sums is None for s_ in self.srcs):
+        if not GN_FOLD or GN_FOLD_PRODUCERS_ONLY or any(s_.sums is None for s_ in self.srcs):
             return None
         a = self.srcs[0]
         return ops.GNSpec([s_.sums for s_ in self.srcs], [s_.C for s_ in self.srcs], self.gamma, self.beta,
