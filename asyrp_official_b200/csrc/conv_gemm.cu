@@ -28,6 +28,9 @@
 
 namespace asyrp {
 
+#ifndef ASYRP_PAIR128_DEFAULT
+#define ASYRP_PAIR128_DEFAULT 1
+#endif
 static constexpr int kMaxSeg = 3;
 static constexpr int kNumEpilogueWarps = 8;   // two warps per TMEM lane quarter, alternating 32-column chunks
 static constexpr int kNumTransformWarps = 8;
@@ -390,7 +393,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
   const int lane = threadIdx.x & 31;
   constexpr uint32_t kBStage = (CTA2 ? BN / 2 : BN) * 128;
   static_assert(!SWAP || (BN == 128 && MT == 2), "swapped-operand variant: 128 channels x 256 pixels");
-  static_assert(!CTA2 || (BN == 256 && MT == 1 && !SWAP), "CTA-pair variant: 2 x 128 pixels x 256 channels");
+  static_assert(!CTA2 || (((BN == 256 && MT == 1) || (BN == 128 && MT == 2)) && !SWAP),
+                "CTA-pair variants: 2 x 128 pixels x 256 channels, 2 x 256 pixels x 128 channels");
   const uint32_t cta_rank = CTA2 ? cluster_ctarank() : 0u;
   constexpr uint32_t kAccCols = SWAP ? MT * 128 : MT * BN;  // fp32 columns of one accumulator set
   constexpr uint32_t kTmemCols = 2 * kAccCols;                // two sets (epilogue / MMA overlap)
@@ -615,9 +619,15 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
                 const uint32_t b_lo = b_lo0 + sb * (kBStage >> 4);
                 if (elect_one()) {
                   if constexpr (CTA2) {
+                    // M = 256: the 128 pixel rows of sub-tile `sub` of BOTH CTAs; N = BN channels, half of the weight
+                    // rows in each CTA's shared memory
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                      umma_f16_w_2cta(d_tmem, a_lo + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc, (accumulate | k) ? 1u : 0u);
+                    for (int sub = 0; sub < MT; ++sub) {
+#pragma unroll
+                      for (int k = 0; k < 4; ++k)
+                        umma_f16_w_2cta(d_tmem + sub * BN, a_lo + sub * sub16 + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc,
+                                        (accumulate | k) ? 1u : 0u);
+                    }
                   } else if constexpr (SWAP) {
                     // M = 128 weight rows, N = all MT*128 pixel rows (uniform 8-row-group pitch across sub-tiles)
 #pragma unroll
@@ -1146,7 +1156,8 @@ struct ConvOp {
 using namespace asyrp;
 
 static const void* conv_kernel_ptr(int BN, int MT, int cta2 = 0) {
-  if (cta2) return reinterpret_cast<const void*>(&conv_gemm_kernel<256, 1, false, true>);
+  if (cta2) return BN == 256 ? reinterpret_cast<const void*>(&conv_gemm_kernel<256, 1, false, true>)
+                             : reinterpret_cast<const void*>(&conv_gemm_kernel<128, 2, false, true>);
   if (BN == 16) return MT == 2 ? reinterpret_cast<const void*>(&conv_gemm_kernel<16, 2>)
                                : reinterpret_cast<const void*>(&conv_gemm_kernel<16, 1>);
   if (BN == 256) return reinterpret_cast<const void*>(&conv_gemm_kernel<256, 1>);
@@ -1219,6 +1230,28 @@ static int cta2_enabled() {  // ASYRP_CTA2=0 / asyrp_set_cta2(0): never use the 
   return g_cta2;
 }
 
+// CTA pairs for the 256 px x 128 ch tile too (instead of the one-CTA swapped-operand tile): each CTA of a pair keeps 64
+// of the 128 weight rows, so a CTA ingests (and writes to shared memory) half the weight bytes per tile.
+// ASYRP_PAIR128=0/1 / asyrp_set_pair128().
+static int g_pair128 = -1;
+static int pair128_enabled() {
+  if (g_pair128 < 0) {
+    const char* e = getenv("ASYRP_PAIR128");
+    g_pair128 = (e != nullptr) ? (e[0] != '0') : ASYRP_PAIR128_DEFAULT;
+  }
+  return g_pair128;
+}
+// Does a conv with this tile configuration run as CTA pairs?  Two horizontally adjacent pixel tiles share each weight
+// tile: needs an even number of pixel tiles per sample (so that the pairing does not depend on the batch) and, at the
+// nominal batch of 16, enough pairs to occupy the 74 TPCs.  The arithmetic per tile is that of the one-CTA kernel.
+// txy: pixel tiles per sample, n_tiles: channel tiles (x sub-pixel phases).
+static int conv_pairs(int bn, int mt, int NB, int txy, int n_tiles) {
+  if (!cta2_enabled() || NB != 1 || txy % 2 != 0 || (txy / 2) * 16 * n_tiles < 64) return 0;
+  if (bn == 256 && mt == 1) return 1;
+  if (bn == 128 && mt == 2) return pair128_enabled();
+  return 0;
+}
+
 // A 3x3/s1 conv whose output is at least 8 wide and 16 tall uses 8x16-pixel sub-tiles fed from one halo tile per
 // 64-channel chunk ("halo" geometry, segment mode 3); otherwise three dx-shifted copies (mode 1).
 static int conv_halo_ok(int H, int W) { return H % 16 == 0 && W % 8 == 0; }
@@ -1286,7 +1319,8 @@ ASYRP_API int asyrp_conv_stats_tiles(int H, int W, int Cout, int has_3x3) {
   conv_config(H, W, Cout, halo, &bn, &mt);
   const int tht = TH * mt;
   const int tiles = ((W + TW - 1) / TW) * ((H + tht - 1) / tht);
-  if (bn == 128 && mt == 2) return tiles * 2;  // swapped-operand kernel: one slot per (tile, warp half)
+  // swapped-operand kernel: one slot per (tile, warp half)
+  if (bn == 128 && mt == 2 && !conv_pairs(bn, mt, NB, tiles, Cout / bn)) return tiles * 2;
   return NB == 1 ? tiles : tiles * 4;
 }
 
@@ -1294,9 +1328,13 @@ ASYRP_API int asyrp_conv_stats_tiles(int H, int W, int Cout, int has_3x3) {
 // 128-channel x 256-pixel tile).  Lets the caller route work that the swapped tile's epilogue handles badly (a
 // residual read through a resample index map: scattered 2-byte loads per lane) to another formulation.
 ASYRP_API int asyrp_conv_tile_config(int H, int W, int Cout, int has_3x3) {
-  int bn, mt;
-  conv_config(H, W, Cout, has_3x3 && conv_halo_ok(H, W), &bn, &mt);
-  return bn * 16 + mt;
+  int bn, mt, TW, TH, NB;
+  const int halo = has_3x3 && conv_halo_ok(H, W);
+  conv_config(H, W, Cout, halo, &bn, &mt);
+  conv_tile_shape(H, W, halo, &TW, &TH, &NB);
+  const int txy = ((W + TW - 1) / TW) * ((H + TH * mt - 1) / (TH * mt));
+  // bit 16: runs as CTA pairs (generic epilogue) — for 128 x 2 that means "not the swapped-operand tile"
+  return bn * 16 + mt + (conv_pairs(bn, mt, NB, txy, Cout / bn) ? (1 << 16) : 0);
 }
 
 // statistics slots per sample written by an up2 conv over an H x W SOURCE image (output 2H x 2W)
@@ -1306,8 +1344,9 @@ ASYRP_API int asyrp_conv_stats_tiles_up2(int H, int W, int Cout) {
   conv_tile_shape(H, W, 1, &TW, &TH, &NB);
   conv_config(H, W, Cout, 1, &bn, &mt, 4);
   const int tht = TH * mt;
-  const int tiles = ((W + TW - 1) / TW) * ((H + tht - 1) / tht) * 4;
-  return (bn == 128 && mt == 2) ? tiles * 2 : tiles;
+  const int txy = ((W + TW - 1) / TW) * ((H + tht - 1) / tht);
+  const int tiles = txy * 4;
+  return (bn == 128 && mt == 2 && !conv_pairs(bn, mt, NB, txy, 4 * (Cout / bn))) ? tiles * 2 : tiles;
 }
 
 ASYRP_API int asyrp_conv_create(const AsyrpConvDesc* d, void** out_op) {
@@ -1340,14 +1379,9 @@ ASYRP_API int asyrp_conv_create(const AsyrpConvDesc* d, void** out_op) {
   p.tiles_n = (d->N + p.NB - 1) / p.NB;
   p.m_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
   p.n_tiles = (d->Cout / op->BN) * (p.up2 ? 4 : 1);
-  {
-    // CTA pairs for the 128 px x 256 ch tiles: two horizontally adjacent pixel tiles share each weight tile.  Needs an
-    // even number of pixel tiles per sample (so that the pairing does not depend on the batch) and, at the nominal
-    // batch of 16, enough pairs to occupy the 74 TPCs.  The arithmetic per tile is that of the one-CTA kernel.
-    const int txy = p.tiles_x * p.tiles_y;
-    op->cta2 = cta2_enabled() && op->BN == 256 && op->MT == 1 && p.NB == 1 && txy % 2 == 0 && !d->weight_batched &&
-               d->a_heads <= 1 && d->out_heads <= 1 && (txy / 2) * 16 * p.n_tiles >= 64;
-  }
+  op->cta2 = !d->weight_batched && d->a_heads <= 1 && d->out_heads <= 1 && !d->out_f32 &&
+             conv_pairs(op->BN, op->MT, p.NB, p.tiles_x * p.tiles_y, p.n_tiles);
+  const bool swapped = op->BN == 128 && op->MT == 2 && !op->cta2;  // the one-CTA swapped-operand tile
   {
     // x / dv == umulhi(x, 2^32/dv + 1) for all x with x*dv < 2^32; the largest dividend is the tile count
     const unsigned long long xmax = static_cast<unsigned long long>(p.m_tiles) * p.n_tiles;
@@ -1469,11 +1503,10 @@ ASYRP_API int asyrp_conv_create(const AsyrpConvDesc* d, void** out_op) {
   p.out_heads = d->out_heads > 1 ? d->out_heads : 1;
   p.out_ld = d->Cout * p.out_heads;
   p.out_f32 = d->out_f32;
-  ASYRP_REQUIRE(!d->out_f32 || (d->residual == nullptr && d->stats == nullptr && d->out_planar == nullptr &&
-                                !(op->BN == 128 && op->MT == 2)),
+  ASYRP_REQUIRE(!d->out_f32 || (d->residual == nullptr && d->stats == nullptr && d->out_planar == nullptr && !swapped),
                 "asyrp_conv_create: out_f32 excludes residual / stats / planar output and the swapped-operand tile");
   ASYRP_REQUIRE(p.out_heads == 1 || (d->N % p.out_heads == 0 && d->stats == nullptr && d->out_planar == nullptr &&
-                                     !(op->BN == 128 && op->MT == 2)),
+                                     !swapped),
                 "asyrp_conv_create: out_heads needs N %% heads == 0, no stats / planar output, Cout != 128*odd");
   p.a_stage_bytes = halo ? (((THT + 2) * (p.TW + 2) * 128u + 1023u) / 1024u) * 1024u
                          : (any3 ? THT + 2 : THT) * p.row_bytes;
@@ -1504,13 +1537,13 @@ ASYRP_API int asyrp_conv_create(const AsyrpConvDesc* d, void** out_op) {
   p.planar_c = d->planar_c;
   ASYRP_REQUIRE(d->out_planar == nullptr || (d->planar_c >= 1 && d->planar_c <= 8),
                 "asyrp_conv_create: planar_c=%d out of range", d->planar_c);
-  ASYRP_REQUIRE(!(d->out_planar != nullptr && op->BN == 128 && op->MT == 2),
+  ASYRP_REQUIRE(!(d->out_planar != nullptr && swapped),
                 "asyrp_conv_create: planar output needs Cout == 64 (padded conv_out)");
   p.res = static_cast<const __half*>(d->residual);
   p.res_scale = d->res_scale;
   p.acc_scale = d->acc_scale;
   p.scales = d->scales;
-  ASYRP_REQUIRE(d->scales == nullptr || !(op->BN == 128 && op->MT == 2),
+  ASYRP_REQUIRE(d->scales == nullptr || !swapped,
                 "asyrp_conv_create: device-side scales are not supported by the swapped-operand tile");
   p.res_mode = d->residual != nullptr ? d->res_mode : 0;
   ASYRP_REQUIRE(p.res_mode >= 0 && p.res_mode <= 2, "asyrp_conv_create: res_mode %d", d->res_mode);
@@ -1589,6 +1622,12 @@ ASYRP_API void asyrp_conv_destroy(void* handle) { delete static_cast<ConvOp*>(ha
 // CTA-pair (tcgen05 cta_group::2) variant of the 128 px x 256 ch tile: on by default; affects ops created afterwards
 ASYRP_API int asyrp_set_cta2(int enabled) {
   g_cta2 = enabled ? 1 : 0;
+  return ASYRP_OK;
+}
+// CTA pairs for the 256 px x 128 ch tile (instead of the swapped-operand tile); affects ops created afterwards AND the
+// statistics-slot counts asyrp_conv_stats_tiles*() report — set it before building a plan
+ASYRP_API int asyrp_set_pair128(int enabled) {
+  g_pair128 = enabled < 0 ? -1 : (enabled ? 1 : 0);  // negative: back to the default (ASYRP_PAIR128, else built-in)
   return ASYRP_OK;
 }
 // 1 if `op` runs as CTA pairs

@@ -66,9 +66,11 @@ def conv_stats_tiles(H, W, C, has_3x3):
 
 
 def conv_tile_config(H, W, C, has_3x3):
-    """(BN, MT) of the tile the library uses for this output geometry; (128, 2) is the swapped-operand tile"""
+    """(BN, MT) of the tile the library uses for this output geometry; (128, 2) is the swapped-operand tile, unless the
+    conv runs as CTA pairs with the generic epilogue — then (128, 2, "pair")"""
     v = _lib.load().asyrp_conv_tile_config(H, W, C, int(has_3x3))
-    return v // 16, v % 16
+    cfg = ((v & 0xFFFF) // 16, v % 16)
+    return cfg + ("pair",) if (v >> 16) & 1 and cfg == (128, 2) else cfg
 
 
 def conv_stats_tiles_up2(H, W, C):

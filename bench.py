@@ -251,7 +251,7 @@ def cpu_sample(run, kind, seq, traj_steps, reps=1):
                       f"{torch.get_num_threads()} threads"}, best
 
 
-def eager_gpu(family, key, ckpt, batch, traj_steps, dev, reps=2):
+def eager_gpu(family, key, ckpt, batch, traj_steps, dev, reps=2, golden=None):
     """the reference's modules + denoising_step, eager PyTorch on the B200 (cuDNN/cuBLAS, TF32 convs as torch's
     default): full trajectories at the bench batch"""
     mirror, _ = build_model(family, key, "cpu", ckpt)
@@ -277,9 +277,34 @@ def eager_gpu(family, key, ckpt, batch, traj_steps, dev, reps=2):
         torch.cuda.synchronize()
         if r:
             best = min(best, time.perf_counter() - t0)
+    ref_parity = None
+    gp = os.path.join(GOLD, golden) if golden else None
+    if gp and os.path.exists(gp):
+        # how far the reference's OWN GPU path (cuDNN TF32 convs, torch's default) lands from its CPU fp32 output on
+        # the golden inputs of this workload: the yardstick for the engine's `parity` (same fixture, same noise)
+        gd = np.load(gp)
+        gb = int(gd["batch"])
+        g = torch.Generator().manual_seed(int(gd["x_seed"]))
+        xg = torch.randn(gb, 3, 256, 256, generator=g)
+        gn = torch.Generator().manual_seed(int(gd["noise_seed"]))
+        noises = {i: torch.randn(xg.shape, generator=gn).to(dev) for i in gd["seq"].tolist()}
+        order = [i for i in reversed(seq) if i < int(gd["t_addnoise"])]  # the stochastic steps (eta = 1 below t_addnoise), in loop order
+        orig = torch.randn_like
+        it = iter(order)
+        torch.randn_like = lambda ten, *a, **k: noises[next(it)]
+        try:
+            xr, _ = reference_trajectory(ref, du, xg.to(dev), seq, seq_next, betas, logvar, family == "adm")
+        finally:
+            torch.randn_like = orig
+        gref = torch.from_numpy(gd["x0_sub"])
+        err = (xr.cpu()[..., ::4, ::4] - gref).abs().max().item()
+        m = float(gd["x0_absmax"])
+        ref_parity = {"max_abs": round(err, 5), "max_ref": round(m, 3), "rel": round(err / max(m, 1.0), 7), "batch": gb,
+                      "what": f"{golden}: the reference's eager GPU run (TF32 convs) vs the reference's CPU fp32 run"}
     del ref
     torch.cuda.empty_cache()
     return {"value": round(batch / best, 3), "unit": "img/s", "batch": batch, "s_per_trajectory": round(best, 3),
+            "parity_vs_cpu_reference": ref_parity,
             "how": "baseline/_ref modules + utils.diffusion_utils.denoising_step in the save_image loop "
                    "(diffusion_latent.py:499-520), eager PyTorch on cuda:0, fp32 tensors, "
                    f"cudnn.allow_tf32={torch.backends.cudnn.allow_tf32}, matmul.allow_tf32="
@@ -534,7 +559,7 @@ def main():
     eager = None
     if not args.no_eager_baseline:
         try:
-            eager = eager_gpu(family, key, ckpt, batch, traj_steps, dev)
+            eager = eager_gpu(family, key, ckpt, batch, traj_steps, dev, golden=golden)
         except Exception as e:  # noqa: BLE001
             eager = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
     line = {"metric": METRIC, "value": round(value, 3), "unit": "img/s", "n_gpus": args.gpus, "steps": args.steps,

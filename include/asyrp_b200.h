@@ -135,7 +135,8 @@ typedef struct AsyrpConvDesc {
  * ASYRP_CONV_3x3 segment (selects the 8x16 halo tile geometry when H%16==0 and W%8==0) */
 int asyrp_conv_stats_tiles(int H, int W, int Cout, int has_3x3);
 /* tile configuration the library picks for this output geometry: BN * 16 + MT (BN output channels x MT * 128 pixels per
- * CTA tile; 128 * 16 + 2 is the swapped-operand tile) */
+ * CTA tile; 128 * 16 + 2 is the swapped-operand tile;
+ * bit 16 is set when the conv runs as CTA pairs with the generic epilogue instead) */
 int asyrp_conv_tile_config(int H, int W, int Cout, int has_3x3);
 /* the same for an up2 conv over an H x W source image (0 if the geometry is unsupported) */
 int asyrp_conv_stats_tiles_up2(int H, int W, int Cout);
@@ -143,6 +144,10 @@ int asyrp_conv_stats_tiles_up2(int H, int W, int Cout);
  * every weight tile through `tcgen05.mma.cta_group::2` (M = 256): each SM loads half of the weight rows.  Bit-identical
  * to the one-CTA kernel.  On by default (ASYRP_CTA2=0 or asyrp_set_cta2(0) disables it for ops created afterwards). */
 int asyrp_set_cta2(int enabled);
+/* CTA pairs for the 256 pixel x 128 channel tile as well (each SM keeps 64 of the 128 weight rows) instead of the one-CTA
+ * swapped-operand tile; changes the statistics-slot counts asyrp_conv_stats_tiles*() report, so set it before building
+ * a plan (ASYRP_PAIR128=0/1) */
+int asyrp_set_pair128(int enabled);
 int asyrp_conv_is_cta2(void* op);
 int asyrp_conv_create(const AsyrpConvDesc* desc, void** op); /* encodes TMA descriptors; host only */
 int asyrp_conv_launch(void* op, void* stream);

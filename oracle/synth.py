@@ -56,3 +56,17 @@ def synth_noise(shape, seed=1234):
     g = torch.Generator()
     g.manual_seed(seed)
     return torch.randn(shape, generator=g)
+
+
+def synth_image(shape, seed=77):
+    """a smooth synthetic 'photograph' in [-1, 1]: three octaves of seeded noise, bilinearly upsampled, through tanh
+    (stand-in for the dataset images precompute_pairs inverts, diffusion_latent.py:905-933; there are no datasets here)"""
+    import torch.nn.functional as F
+    g = torch.Generator()
+    g.manual_seed(seed)
+    n, c, h, w = shape
+    img = torch.zeros(shape)
+    for div, amp in ((32, 1.0), (8, 0.5), (2, 0.15)):
+        z = torch.randn(n, c, max(2, h // div), max(2, w // div), generator=g)
+        img = img + amp * F.interpolate(z, size=(h, w), mode="bilinear", align_corners=True)
+    return torch.tanh(img)

@@ -18,6 +18,8 @@ Fixtures (npz, fp32):
   adm_afhq_happy_traj40.npz            configs[2] at B=1: iDDPM-AFHQ, 'dog_happy' DeltaBlock, 40 steps
   ddpm_church_gothic_traj40.npz        configs[3] at B=1: DDPM LSUN-Church (same UNet as CelebA), 'church_gothic' block
   adm_imagenet_traj50.npz              configs[4] at B=1: ADM-ImageNet, seeded DeltaBlock, 50 steps
+  ddpm_celeba_bounded_t400.npz         the pipeline in the image range (|x| < 2 throughout): inversion of a synthetic image
+                                    + 40-step edit at --t_0 400 with conv_out scaled by 0.03; full x_T and x_0 (--traj bounded)
                                     (trajectory fixtures: stride-4 subsample of x_0, |x_0| max, seeds, sequence)
 """
 import argparse
@@ -284,10 +286,57 @@ def trajectory_fixture(name, family, cfg, key, B, n_step, chunk=4):
     print(f"{name} ok ({time.time() - t0:.1f}s): |x_0|max={xf.abs().max():.2f}")
 
 
+@torch.no_grad()
+def bounded_fixture(gamma=0.03, t_0=400, n_step=40, t_edit=200, t_addnoise=80):
+    """The Asyrp pipeline in the IMAGE range, at full size: DDPM CelebA-HQ 256x256, synthetic seeded weights + the shipped
+    'smiling' DeltaBlock, conv_out (weight and bias) scaled by `gamma`, --t_0 400 (a flag of the reference,
+    1/sqrt(alpha-bar_400) = 2.2 instead of 160): precompute_pairs' inversion of a synthetic image in [-1, 1]
+    (diffusion_latent.py:922-933), then save_image's edit loop (:499-520) from that x_T.  Everything stays within
+    |x| < 2 (the UNet sees ordinary O(1) inputs at every step), so the engine-vs-reference error of this fixture is
+    an ABSOLUTE number on an O(1)-range image.  Reference's own modules + denoising_step; oracle must agree bit for bit."""
+    t0 = time.time()
+    cfg = o_ddpm.CELEBA_CFG
+    shapes = o_ddpm.ddpm_param_shapes(cfg, 1)
+    model = ref_ddpm(cfg, 1)
+    sd = synth.synth_state_dict(shapes, seed=1234, style="torch_default")
+    for k, v in shipped_delta_block("celeba").items():
+        sd["layer_0." + k] = v
+    sd["conv_out.weight"] = sd["conv_out.weight"] * gamma
+    sd["conv_out.bias"] = sd["conv_out.bias"] * gamma
+    load_checked(model, shapes, sd)
+    fwd = lambda *a, **k: o_ddpm.ddpm_forward(sd, cfg, *a, **k)  # noqa: E731
+    x0 = synth.synth_image((1, 3, 256, 256), seed=77).to(torch.float16).float()  # stored as fp16: exactly representable
+    betas = o_smp.make_betas()
+    seq, seq_next = o_smp.make_sequences(t_0, n_step)
+    logv = o_smp.make_logvar(o_smp.get_beta_schedule(beta_start=1e-4, beta_end=0.02, num_diffusion_timesteps=1000))
+    xr, xo = x0.clone(), x0.clone()
+    for i, j in zip(seq_next[1:], seq[1:]):
+        t, tn = torch.ones(1) * i, torch.ones(1) * j
+        xr = ref_du.denoising_step(xr, t=t, t_next=tn, models=model, logvars=logv, sampling_type="ddim", b=betas, eta=0,
+                                   learn_sigma=False)[0]
+        xo = o_smp.denoising_step(xo, t, tn, model=fwd, logvars=logv, b=betas, eta=0.0)[0]
+    assert torch.equal(xr, xo), (xr - xo).abs().max()
+    x_T = xr
+    gn = torch.Generator().manual_seed(4321)
+    noises = {i: torch.randn(x0.shape, generator=gn) for i in seq}
+    rec = []
+    xf = ref_trajectory(model, x_T, betas, seq, seq_next, t_edit, t_addnoise, False, noises, rec)
+    xo = o_smp.run_trajectory(fwd, x_T, betas=betas, seq=seq, seq_next=seq_next, t_edit=t_edit, t_addnoise=t_addnoise,
+                              index=0, hs_coeff=(1.0, 1.0), noises=noises, logvars=logv)
+    assert torch.equal(xf, xo), (xf - xo).abs().max()
+    np.savez_compressed(os.path.join(HERE, "ddpm_celeba_bounded_t400.npz"), x0_in=x0.to(torch.float16).numpy(),
+                        x_T=x_T.numpy(), x0_out=xf.numpy(), gamma=np.array(gamma), t_0=np.array(t_0), seq=np.array(seq),
+                        t_edit=np.array(t_edit), t_addnoise=np.array(t_addnoise), noise_seed=np.array(4321),
+                        x0t_absmax=np.array([r[1].abs().max().item() for r in rec]))
+    print(f"ddpm_celeba_bounded_t400 ok ({time.time() - t0:.0f}s): |x_0 in| {x0.abs().max():.3f} |x_T| {x_T.abs().max():.3f} "
+          f"|x_0 out| {xf.abs().max():.3f} |x_0 out - x_0 in| {(xf - x0).abs().max():.3f} (rms {(xf - x0).pow(2).mean().sqrt():.3f}) "
+          f"max_t |x0_t| {max(r[1].abs().max().item() for r in rec):.3f}")
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--full", action="store_true", help="also the 256x256 fixtures (minutes of CPU time)")
-    ap.add_argument("--traj", default="", help="comma list of trajectory fixtures: celeba16, afhq, imagenet, church")
+    ap.add_argument("--traj", default="", help="comma list of trajectory fixtures: celeba16, afhq, imagenet, church, bounded")
     ap.add_argument("--skip-mini", action="store_true")
     args = ap.parse_args()
     torch.set_num_threads(os.cpu_count())
@@ -300,6 +349,8 @@ if __name__ == "__main__":
             trajectory_fixture("adm_imagenet_traj50", "adm", o_adm.IMAGENET_HP, "imagenet", 1, 50)
         elif t == "church":
             trajectory_fixture("ddpm_church_gothic_traj40", "ddpm", o_ddpm.CELEBA_CFG, "church", 1, 40)
+        elif t == "bounded":
+            bounded_fixture()
         else:
             raise SystemExit(f"unknown trajectory fixture {t}")
     if args.skip_mini:

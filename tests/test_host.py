@@ -25,7 +25,13 @@ def test_library_exports_every_declared_symbol():
     assert lib.asyrp_last_error() is not None
     # pure host helper (no device): tile bookkeeping for the GroupNorm partial sums
     assert lib.asyrp_conv_stats_tiles(256, 256, 256, 0) == 512  # 128x256 tiles
+    lib.asyrp_set_pair128(0)
     assert lib.asyrp_conv_stats_tiles(256, 256, 128, 1) == 512  # swapped 128x256 tiles, two slots each
+    assert lib.asyrp_conv_tile_config(256, 256, 128, 1) == 128 * 16 + 2
+    lib.asyrp_set_pair128(1)
+    assert lib.asyrp_conv_stats_tiles(256, 256, 128, 1) == 256  # CTA pairs, 256 px x 128 ch per CTA: one slot per tile
+    assert lib.asyrp_conv_tile_config(256, 256, 128, 1) == 128 * 16 + 2 + (1 << 16)
+    lib.asyrp_set_pair128(-1)
     assert lib.asyrp_conv_stats_tiles(8, 8, 512, 1) == 4        # 2 samples per tile, one slot per lane quarter
 
 

@@ -518,6 +518,76 @@ def test_cta_pair_kernel_matches_reference_and_one_cta_kernel(cuda_device, case)
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]), "CTA-pair kernel != one-CTA kernel"
 
 
+@pytest.mark.parametrize("case", ["plain", "fused_shortcut", "up2"])
+def test_pair128_kernel_matches_reference_and_swapped_kernel(cuda_device, case):
+    """CTA-pair variant of the 256 px x 128 ch tile (cta_group::2, M = 2 x 128 pixels, 64 weight rows per CTA, generic
+    epilogue) against the fp64 formula and against the one-CTA swapped-operand kernel it replaces (same K order per
+    tile; the GroupNorm partial sums use one slot per tile instead of two)"""
+    ops = _ops()
+    lib = ops._lib.load()
+    g = torch.Generator().manual_seed(37)
+    N, C = 3, 128
+    kw = {}
+    if case == "plain":
+        H = W = 64
+        x, w = _rand((N, C, H, W), g), _rand((C, C, 3, 3), g, 1.0 / math.sqrt(9 * C))
+        eb, res = _rand((N, C), g), _rand((N, C, H, W), g)
+        ref = 0.75 * (F.conv2d(_h(x), _h(w), padding=1) + eb.double()[:, :, None, None]) + 1.5 * _h(res)
+        segs = [(_nhwc_half(x, cuda_device), ops.MODE_3x3)]
+        wp = ops.pack_conv_weight(w)
+        kw = dict(ebias=eb.to(cuda_device), ebias_stride=C, residual=_nhwc_half(res, cuda_device), res_scale=1.5,
+                  acc_scale=0.75)
+        shape = (N, H, W, C)
+    elif case == "fused_shortcut":
+        H = W = 64
+        h, x1, x2 = _rand((N, C, H, W), g), _rand((N, C, H, W), g), _rand((N, C, H, W), g)
+        aff = torch.stack([_rand((N, C), g) * 0.5 + 1.0, _rand((N, C), g) * 0.5], dim=-1).contiguous()
+        w3 = _rand((C, C, 3, 3), g, 1.0 / math.sqrt(9 * C))
+        w1 = _rand((C, 2 * C, 1, 1), g, 1.0 / math.sqrt(2 * C))
+        y = _h(h) * aff[..., 0].double()[:, :, None, None] + aff[..., 1].double()[:, :, None, None]
+        y = _h((y * torch.sigmoid(y)).float())
+        ref = F.conv2d(y, _h(w3), padding=1) + F.conv2d(torch.cat([_h(x1), _h(x2)], 1), _h(w1))
+        segs = [(_nhwc_half(h, cuda_device), ops.MODE_3x3, aff.to(cuda_device), 0, 1),
+                (_nhwc_half(x1, cuda_device), ops.MODE_1x1), (_nhwc_half(x2, cuda_device), ops.MODE_1x1)]
+        wp = torch.cat([ops.pack_conv_weight(w3), ops.pack_conv_weight(w1[:, :C]), ops.pack_conv_weight(w1[:, C:])], 1)
+        shape = (N, H, W, C)
+    else:
+        H = W = 32
+        x, w = _rand((N, C, H, W), g), _rand((C, C, 3, 3), g, 1.0 / math.sqrt(9 * C))
+        ref = F.conv2d(F.interpolate(_h(x), scale_factor=2.0, mode="nearest"), w.double(), padding=1)
+        segs = [(_nhwc_half(x, cuda_device), ops.MODE_3x3)]
+        wp = ops.pack_upconv_weight(w)
+        kw = dict(up2=True)
+        shape = (N, 2 * H, 2 * W, C)
+    outs = []
+    try:
+        for on in (1, 0):
+            lib.asyrp_set_pair128(on)
+            cfg = ops.conv_tile_config(64, 64, C, True) if case != "up2" else None
+            assert cfg is None or cfg == ((128, 2, "pair") if on else (128, 2)), cfg
+            out = torch.zeros(shape, dtype=torch.float16, device=cuda_device)
+            tiles = ops.conv_stats_tiles_up2(32, 32, C) if case == "up2" else ops.conv_stats_tiles(64, 64, C, 1)
+            stats = torch.zeros(N, tiles, C // 2, 2, dtype=torch.float32, device=cuda_device)
+            op = ops.ConvOp(segs, wp.contiguous().to(cuda_device), out=out, stats=stats, **kw)
+            assert op.cta2 == bool(on), f"{case}: CTA-pair selection {op.cta2} with pair128={on}"
+            op.launch()
+            op.launch()
+            torch.cuda.synchronize()
+            outs.append((out, stats))
+    finally:
+        lib.asyrp_set_pair128(-1)
+    tol = 2.5e-3
+    for out, stats in outs:
+        _check(_from_nhwc(out), ref, tol, f"pair128 {case}")
+        st = stats.sum(dim=1).cpu().double()
+        sref = _stats_ref(ref)
+        assert (st - sref).abs().max().item() <= 3e-3 * sref.abs().max().item() + 1e-3
+    assert outs[0][1].shape[1] * 2 == outs[1][1].shape[1], "one statistics slot per tile (pair) vs two (swapped)"
+    # the same products are accumulated in the same K order by both kernels
+    d = (outs[0][0].float() - outs[1][0].float()).abs().max().item()
+    assert d <= 2.0 ** -9 * ref.abs().max().item(), f"pair128 vs swapped kernel: {d}"
+
+
 @pytest.mark.parametrize("Co,fused", [(3, False), (6, True)])
 def test_conv_out_narrow_tile(cuda_device, Co, fused):
     """conv_out as a 16-wide N tile (BN=16): 3 / 6 real channels, fp32 planar store, bias, optional fused GN+SiLU"""
