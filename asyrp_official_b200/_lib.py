@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libasyrp_b200.so")
+# ASYRP_LIB_SUFFIX selects a diagnostic build made with the same suffix (asyrp_official_b200/build.py); default: the product
+LIB_PATH = os.path.join(_HERE, f"libasyrp_b200{os.environ.get('ASYRP_LIB_SUFFIX', '')}.so")
 
 c_void_p, c_int, c_float = C.c_void_p, C.c_int, C.c_float
 
@@ -55,6 +56,7 @@ SIGNATURES = {
     "asyrp_conv_tile_config": (c_int, [c_int, c_int, c_int, c_int]),
     "asyrp_set_cta2": (c_int, [c_int]),
     "asyrp_set_pair128": (c_int, [c_int]),
+    "asyrp_set_silu_tanh": (c_int, [c_int]),
     "asyrp_conv_is_cta2": (c_int, [c_void_p]),
     "asyrp_conv_create": (c_int, [C.POINTER(AsyrpConvDesc), C.POINTER(c_void_p)]),
     "asyrp_conv_launch": (c_int, [c_void_p, c_void_p]),

@@ -9,7 +9,9 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libasyrp_b200.so")
+# ASYRP_LIB_SUFFIX / ASYRP_EXTRA_NVCC_FLAGS: diagnostic builds next to the product library (scripts/conv_trace.py)
+SUFFIX = os.environ.get("ASYRP_LIB_SUFFIX", "")
+LIB = os.path.join(HERE, f"libasyrp_b200{SUFFIX}.so")
 SOURCES = ["common.cu", "conv_gemm.cu", "pointwise.cu", "attention.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -21,7 +23,7 @@ def _stale():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.abspath(__file__)]
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if not f.endswith(".o")] + [os.path.abspath(__file__)]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
@@ -35,8 +37,9 @@ def build_library(force=False, verbose=False):
         path = os.path.join(CSRC, src)
         if not os.path.exists(path):
             continue
-        obj = os.path.join(CSRC, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", path, "-o", obj] + (["-Xptxas", "-v"] if verbose else [])
+        obj = os.path.join(CSRC, src.replace(".cu", f"{SUFFIX}.o"))
+        cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("ASYRP_EXTRA_NVCC_FLAGS", "").split(), "-c", path, "-o", obj] + \
+            (["-Xptxas", "-v"] if verbose else [])
         subprocess.run(cmd, check=True)
         objs.append(obj)
     subprocess.run([nvcc, "-shared", "-cudart", "static", "-o", LIB, *objs], check=True)

@@ -29,7 +29,7 @@
 namespace asyrp {
 
 #ifndef ASYRP_PAIR128_DEFAULT
-#define ASYRP_PAIR128_DEFAULT 1
+#define ASYRP_PAIR128_DEFAULT 0
 #endif
 static constexpr int kMaxSeg = 3;
 static constexpr int kNumEpilogueWarps = 8;   // two warps per TMEM lane quarter, alternating 32-column chunks
@@ -119,7 +119,22 @@ struct ConvParams {
   // K-loop order: entries (segment << 6 | 64-channel chunk), see asyrp_conv_create().
   int n_sched;
   uint8_t sched[64];
+#ifdef ASYRP_TRACE
+  long long* trace;  // diagnostic build only: [CTA][kTraceRoles][kTraceLen] clock64() stamps, see scripts/conv_trace.py
+#endif
 };
+// Pipeline timeline of a diagnostic build (-DASYRP_TRACE, scripts/conv_trace.py): one elected lane per role stamps
+// clock64() at its hand-off points; compiled out of the product library.
+#ifdef ASYRP_TRACE
+static constexpr int kTraceRoles = 10, kTraceLen = 128;
+#define ASYRP_TRACE_STAMP(role, idx)                                                                    \
+  do {                                                                                                  \
+    if (p.trace != nullptr && lane == 0 && (idx) < kTraceLen)                                           \
+      p.trace[(static_cast<size_t>(blockIdx.x) * kTraceRoles + (role)) * kTraceLen + (idx)] = clock64(); \
+  } while (0)
+#else
+#define ASYRP_TRACE_STAMP(role, idx) do { } while (0)
+#endif
 
 __device__ __forceinline__ int fast_div(int x, uint32_t mul, int d) {
   // mul == 0: d == 1; mul == 1: range too large for the 32-bit multiply-high (huge batches) -> hardware division
@@ -167,7 +182,8 @@ __device__ __forceinline__ void transform_pixels(uint8_t* stage, int px, int jl,
       float2 f = __half22float2(h2[e]);
       f.x = fmaf(ca[2 * e], f.x, cb[2 * e]);
       f.y = fmaf(ca[2 * e + 1], f.y, cb[2 * e + 1]);
-      if (act) { f.x = silu_fast(f.x); f.y = silu_fast(f.y); }
+      if (act == 2) { f.x = silu_tanh_half(f.x); f.y = silu_tanh_half(f.y); }  // (ca, cb) already halved
+      else if (act) { f.x = silu_fast(f.x); f.y = silu_fast(f.y); }
       h2[e] = inimg[k] ? __floats2half2_rn(f.x, f.y) : __floats2half2_rn(0.f, 0.f);
     }
   }
@@ -195,18 +211,33 @@ __device__ __forceinline__ void transform_fast(uint32_t base, uint32_t vld, uint
       u[k] = lds128(base + k * 4096);
     }
   }
+  if (act == 2) {  // one-MUFU SiLU, (ca, cb) already halved: 4 instead of 7.5 instructions per element
 #pragma unroll
-  for (int k = 0; k < U; ++k) {
-    __half2* h2 = reinterpret_cast<__half2*>(&u[k]);
+    for (int k = 0; k < U; ++k) {
+      __half2* h2 = reinterpret_cast<__half2*>(&u[k]);
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      float2 f = __half22float2(h2[e]);
-      f.x = fmaf(ca[2 * e], f.x, cb[2 * e]);
-      f.y = fmaf(ca[2 * e + 1], f.y, cb[2 * e + 1]);
-      if (act) { f.x = silu_fast(f.x); f.y = silu_fast(f.y); }
-      h2[e] = __floats2half2_rn(f.x, f.y);
+      for (int e = 0; e < 4; ++e) {
+        float2 f = __half22float2(h2[e]);
+        f.x = silu_tanh_half(fmaf(ca[2 * e], f.x, cb[2 * e]));
+        f.y = silu_tanh_half(fmaf(ca[2 * e + 1], f.y, cb[2 * e + 1]));
+        h2[e] = __floats2half2_rn(f.x, f.y);
+      }
+      if (CHK && !((img >> k) & 1u)) u[k] = make_uint4(0u, 0u, 0u, 0u);
     }
-    if (CHK && !((img >> k) & 1u)) u[k] = make_uint4(0u, 0u, 0u, 0u);
+  } else {
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      __half2* h2 = reinterpret_cast<__half2*>(&u[k]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float2 f = __half22float2(h2[e]);
+        f.x = fmaf(ca[2 * e], f.x, cb[2 * e]);
+        f.y = fmaf(ca[2 * e + 1], f.y, cb[2 * e + 1]);
+        if (act) { f.x = silu_fast(f.x); f.y = silu_fast(f.y); }
+        h2[e] = __floats2half2_rn(f.x, f.y);
+      }
+      if (CHK && !((img >> k) & 1u)) u[k] = make_uint4(0u, 0u, 0u, 0u);
+    }
   }
 #pragma unroll
   for (int k = 0; k < U; ++k)
@@ -307,7 +338,11 @@ __device__ __noinline__ void load_resampled_residual(__half2 (&rv)[16], const __
 // TW x (MT*128/TW) tile); this warp drains the 32-pixel column chunks half, half+2, ...  TWS = log2(TW).
 // RES: the residual is read through a resample index map (ADM up / down blocks); a separate instantiation so that the
 // common one (the hot loop of 55 % of the conv time, instruction-issue bound) carries no extra live registers
-template <int TWS, int MT, bool RES>
+// RESM: 0 no residual (every DDPM layer on this tile: identity skips and shortcuts are K columns), 1 residual with the
+// output's geometry, 2 resampled residual.  Separate instantiations: the residual prefetch registers and its address
+// arithmetic pushed the common no-residual loop over the 96-register budget of a 608-thread CTA (spills to local memory,
+// with an L1 of ~28 KB next to 227 KB of shared memory).
+template <int TWS, int MT, int RESM>
 __device__ __forceinline__ void swap_epilogue(const ConvParams& p, uint32_t taddr, int half, size_t obase,
                                               int row_stride, int cout, int lane_off, uint32_t sel, float eb,
                                               size_t rbase, int rrow, float& s1, float& s2) {
@@ -324,24 +359,22 @@ __device__ __forceinline__ void swap_epilogue(const ConvParams& p, uint32_t tadd
     tmem_ld_32x32(taddr + cc * 32, r);
     // element offset of the chunk's first pixel
     const size_t o0 = obase + static_cast<size_t>(cc * kRows) * row_stride;
-    __half2 rv[16];
-    if (resp != nullptr) {  // all residual loads first: independent of the stores below
-      if constexpr (!RES) {
-        const __half* rp = resp + o0;
+    [[maybe_unused]] __half2 rv[RESM != 0 ? 16 : 1];
+    if constexpr (RESM == 1) {  // all residual loads first: independent of the stores below
+      const __half* rp = resp + o0;
 #pragma unroll
-        for (int i = 0; i < 32; i += 2)
-          rv[i >> 1] = __halves2half2(rp[(i >> TWS) * row_stride + (i & (TW - 1)) * cout],
-                                      rp[((i + 1) >> TWS) * row_stride + ((i + 1) & (TW - 1)) * cout]);
-      } else {
-        // ADM up / down blocks only: kept out of line so that the common path's register allocation is untouched
-        load_resampled_residual<TWS>(rv, resp + rbase, p.res_mode, cc * kRows, rrow, cout);
-      }
+      for (int i = 0; i < 32; i += 2)
+        rv[i >> 1] = __halves2half2(rp[(i >> TWS) * row_stride + (i & (TW - 1)) * cout],
+                                    rp[((i + 1) >> TWS) * row_stride + ((i + 1) & (TW - 1)) * cout]);
+    } else if constexpr (RESM == 2) {
+      // ADM up / down blocks only: kept out of line so that the common path's register allocation is untouched
+      load_resampled_residual<TWS>(rv, resp + rbase, p.res_mode, cc * kRows, rrow, cout);
     }
     tmem_ld_wait();
     float v[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = fmaf(__uint_as_float(r[i]), scale, eb);
-    if (resp != nullptr) {
+    if constexpr (RESM != 0) {
 #pragma unroll
       for (int i = 0; i < 32; i += 2) {
         const float2 f = __half22float2(rv[i >> 1]);
@@ -476,6 +509,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
     {
       int sa = 0, sl = 0;      // heavy / light ring cursors
       uint32_t pa = 0, pl = 0;
+      [[maybe_unused]] int tr_n = 0;
       for (int w = worker0; w < n_work; w += n_workers) {
         const int tile = own_tile(w);
         const TileCoord tc = tile_coord(p, tile);
@@ -491,6 +525,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
             for (int cp = 0; cp < ncopies; ++cp) {
               const int slot = lt ? p.a_stages + sl : sa;
               mbar_wait_suspend(&emptyA[slot], (lt ? pl : pa) ^ 1);
+              ASYRP_TRACE_STAMP(0, tr_n);
+              ++tr_n;
               uint8_t* dst = lt ? sL + sl * p.l_stage_bytes : sA + sa * p.a_stage_bytes;
               int c0 = ch * 64, c1, c2 = n0, c3 = 0, c4;
               if (sg.mode == 3) {
@@ -571,11 +607,14 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
       int sa = 0, sl = 0, sb = 0;
       uint32_t pa = 0, pl = 0, pb = 0;
       int it = 0;
+      [[maybe_unused]] int tr_n = 0;
       for (int w = worker0; w < n_work; w += n_workers, ++it) {
         const int tile = own_tile(w);
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
+        ASYRP_TRACE_STAMP(5, it);
         mbar_wait_suspend(&tempty[acc], acc_phase ^ 1);
+        ASYRP_TRACE_STAMP(6, it);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * kAccCols;
         int up_a = 0, up_b = 0;  // up2: sub-pixel phase of this tile = first tap (ky, kx) of its 2x2 kernel
@@ -608,7 +647,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
           {
             for (int cp = 0; cp < ncopies; ++cp) {
               const int slot = lt ? p.a_stages + sl : sa;
+              ASYRP_TRACE_STAMP(3, tr_n);
               mbar_wait((p.any_transform || CTA2) ? &readyA[slot] : &fullA[slot], lt ? pl : pa);
+              ASYRP_TRACE_STAMP(4, tr_n);
+              ++tr_n;
               tc_fence_after();
               uint32_t a_lo =
                   umma_desc_lo(smem_u32(lt ? sL + sl * p.l_stage_bytes : sA + sa * p.a_stage_bytes)) + first16;
@@ -651,6 +693,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
               if (elect_one()) {
                 if constexpr (CTA2) umma_commit_2cta(&emptyA[slot]); else umma_commit(&emptyA[slot]);
               }
+              ASYRP_TRACE_STAMP(9, tr_n - 1);
               if (lt) {
                 if (++sl == p.l_stages) { sl = 0; pl ^= 1; }
               } else {
@@ -693,6 +736,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
       }
       int sa = 0, sl = 0;
       uint32_t pa = 0, plt = 0;
+      [[maybe_unused]] int tr_n = 0;
       // In-kernel GroupNorm: lane g of transform warp s computes (mean, rstd) of group g of segment s for the sample of a
       // tile, ONE tile ahead (the buffer of tile i+1 is written while tile i is transformed; the named barrier at the
       // top of tile i+1 publishes it).  fp64 like gn_finalize_kernel; 32 x nseg threads per tile, not every thread.
@@ -742,9 +786,14 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
             } else if (sg.gn_gamma != nullptr) {  // GroupNorm finalise in place of the table (NB == 1 by construction)
               gn_affine8(sg, s_gstat + ((git & 1) * kMaxSeg + s) * 32, n0 < p.N ? n0 : 0, ch * 64 + jl * 8, ca, cb);
             }
+            if (sg.act == 2) {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) { ca[k] *= 0.5f; cb[k] *= 0.5f; }
+            }
             for (int cp = 0; cp < ncopies; ++cp) {
               const int slot = lt ? p.a_stages + sl : sa;
               mbar_wait_suspend(&fullA[slot], lt ? plt : pa);
+              if (warp == kWarpT) ASYRP_TRACE_STAMP(1, tr_n);
               if (sg.affine != nullptr || sg.gn_gamma != nullptr) {
                 uint8_t* stage = lt ? sL + sl * p.l_stage_bytes : sA + sa * p.a_stage_bytes;
                 const int xoff = sg.mode == 3 ? -1 : (sg.mode == 1 ? cp - 1 : 0);
@@ -815,7 +864,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
                         float2 f = __half22float2(h2[k]);
                         f.x = fmaf(ca[2 * k], f.x, cb[2 * k]);
                         f.y = fmaf(ca[2 * k + 1], f.y, cb[2 * k + 1]);
-                        if (sg.act) { f.x = silu_fast(f.x); f.y = silu_fast(f.y); }
+                        if (sg.act == 2) { f.x = silu_tanh_half(0.5f * f.x); f.y = silu_tanh_half(0.5f * f.y); }
+                        else if (sg.act) { f.x = silu_fast(f.x); f.y = silu_fast(f.y); }
                         h2[k] = __floats2half2_rn(f.x, f.y);
                       }
                     }
@@ -825,6 +875,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
                 fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
               }
               __syncwarp();
+              if (warp == kWarpT) ASYRP_TRACE_STAMP(2, tr_n);
+              ++tr_n;
               if (lane == 0) {
                 if constexpr (CTA2) mbar_arrive_remote(mapa_shared(smem_u32(&readyA[slot]), 0u));
                 else mbar_arrive(&readyA[slot]);
@@ -880,6 +932,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
       }
 
       mbar_wait_suspend(&tfull[acc], acc_phase);
+      if (warp == 2) ASYRP_TRACE_STAMP(7, it);
       tc_fence_after();
       if constexpr (SWAP) {
         // thread = output channel (TMEM lane), registers = 32 consecutive pixels of the 8(16)-wide x 32(16)-tall
@@ -896,11 +949,16 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
         const size_t obase = ((static_cast<size_t>(tn) * OH + ty * THT * ps + pa) * OW + tx * p.TW * ps + pb) * p.Cout + c;
         float s1 = 0.f, s2 = 0.f;
         const uint32_t tq = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kAccCols;
-        if (p.res_mode == 0) {
+        if (p.res == nullptr) {
           if (p.TW == 8)
-            swap_epilogue<3, MT, false>(p, tq, half, obase, row_stride, pix_stride, lane_off, sel, eb, 0, 0, s1, s2);
+            swap_epilogue<3, MT, 0>(p, tq, half, obase, row_stride, pix_stride, lane_off, sel, eb, 0, 0, s1, s2);
           else
-            swap_epilogue<4, MT, false>(p, tq, half, obase, row_stride, pix_stride, lane_off, sel, eb, 0, 0, s1, s2);
+            swap_epilogue<4, MT, 0>(p, tq, half, obase, row_stride, pix_stride, lane_off, sel, eb, 0, 0, s1, s2);
+        } else if (p.res_mode == 0) {
+          if (p.TW == 8)
+            swap_epilogue<3, MT, 1>(p, tq, half, obase, row_stride, pix_stride, lane_off, sel, eb, 0, 0, s1, s2);
+          else
+            swap_epilogue<4, MT, 1>(p, tq, half, obase, row_stride, pix_stride, lane_off, sel, eb, 0, 0, s1, s2);
         } else {
           // residual source geometry for res_mode 1 (half resolution) / 2 (double resolution)
           const int rW = p.res_mode == 1 ? (p.W >> 1) : (p.W << 1), rH = p.res_mode == 1 ? (p.H >> 1) : (p.H << 1);
@@ -910,9 +968,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
                   ? ((static_cast<size_t>(tn) * rH + ((ty * THT) >> 1)) * rW + ((tx * p.TW) >> 1)) * p.Cout + c
                   : ((static_cast<size_t>(tn) * rH + ty * THT * 2) * rW + tx * p.TW * 2) * p.Cout + c;
           if (p.TW == 8)
-            swap_epilogue<3, MT, true>(p, tq, half, obase, row_stride, pix_stride, lane_off, sel, eb, rbase, rrow, s1, s2);
+            swap_epilogue<3, MT, 2>(p, tq, half, obase, row_stride, pix_stride, lane_off, sel, eb, rbase, rrow, s1, s2);
           else
-            swap_epilogue<4, MT, true>(p, tq, half, obase, row_stride, pix_stride, lane_off, sel, eb, rbase, rrow, s1, s2);
+            swap_epilogue<4, MT, 2>(p, tq, half, obase, row_stride, pix_stride, lane_off, sel, eb, rbase, rrow, s1, s2);
         }
         if (p.stats != nullptr) {
           // channel pair = lanes (2j, 2j+1); each (tile, half) owns one slot: nothing to reduce across warps
@@ -954,11 +1012,15 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
 #pragma unroll 1
       for (int cc = half; cc < BN / 32; cc += 2) {
         const int c0 = nt * BN + cc * 32;
-        float ws[32];  // per-lane partial statistics of this chunk, summed over the sub-tiles
-#pragma unroll
-        for (int j = 0; j < 32; ++j) ws[j] = 0.f;
+        // statistics of this chunk: slot `lane` (see below) summed over the sub-tiles.  Reduced across the lanes once per
+        // sub-tile: per-lane partial sums kept alive across the sub-tile loop (32 more registers next to r[] and v[])
+        // spill, and with 227 KB of shared memory carved out the L1 that would catch the spills is ~28 KB
+        float wtot = 0.f;
 #pragma unroll 1
         for (int sub = 0; sub < MT; ++sub) {
+          float ws[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) ws[j] = 0.f;
           const int y = ty * THT + sub * p.TH + yy;
           const bool valid = (x < p.W) && (y < p.H) && (n < p.N);
           // output row of this pixel: batch entry n may be a (sample, head) pair writing a channel slice
@@ -1088,26 +1150,28 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_gemm_kernel(const __grid_
               }
             }
           }
-        }  // sub
-        if (p.stats != nullptr && p.NB == 1) {
-          // recursive-halving reduce-scatter over the 32 lanes: afterwards ws[0] on lane L is the total of slot L
+          if (p.stats != nullptr && p.NB == 1) {
+            // recursive-halving reduce-scatter over the 32 lanes: afterwards ws[0] on lane L is the total of slot L
 #pragma unroll
-          for (int h = 16; h >= 1; h >>= 1) {
-            const bool up = (lane & h) != 0;
+            for (int h = 16; h >= 1; h >>= 1) {
+              const bool up = (lane & h) != 0;
 #pragma unroll
-            for (int i = 0; i < h; ++i) {
-              const float send = up ? ws[i] : ws[i + h];
-              const float keep = up ? ws[i + h] : ws[i];
-              ws[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+              for (int i = 0; i < h; ++i) {
+                const float send = up ? ws[i] : ws[i + h];
+                const float keep = up ? ws[i + h] : ws[i];
+                ws[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+              }
             }
+            wtot += ws[0];
           }
-          st[(q * (BN / 32) + cc) * 32 + lane] = ws[0];
-        }
+        }  // sub
+        if (p.stats != nullptr && p.NB == 1) st[(q * (BN / 32) + cc) * 32 + lane] = wtot;
       }  // cc
       }  // !SWAP
       // accumulator fully drained into registers/global: release it to the MMA warp
       tc_fence_before();
       __syncwarp();
+      if (warp == 2) ASYRP_TRACE_STAMP(8, it);
       if (lane == 0) {
         if constexpr (CTA2) mbar_arrive_remote(mapa_shared(smem_u32(&tempty[acc]), 0u));
         else mbar_arrive(&tempty[acc]);
@@ -1240,6 +1304,20 @@ static int pair128_enabled() {
     g_pair128 = (e != nullptr) ? (e[0] != '0') : ASYRP_PAIR128_DEFAULT;
   }
   return g_pair128;
+}
+// The fused operand transform evaluates SiLU with ONE special-function op (tanh.approx.f32, 11 bits: absolute error
+// <= 2^-12 |x|, the size of the fp16 rounding the operand receives anyway) instead of ex2 + rcp.  The pipeline timeline
+// (scripts/conv_trace.py, profiles/r2_conv_pipeline_trace.md) shows the transform of a 3x3 stage taking as long as its 36
+// MMAs (4.5-5.0k vs 4.6k cycles), the tensor pipe waiting for "stage ready" 10-15 % of the time; with one MUFU and 4
+// instead of 7.5 instructions per element it takes 3.0k and the wait halves: +4.3 % images/s, end-to-end error
+// 3.4e-4 -> 4.0e-4 of max|x_0| on the bench fixture.  ASYRP_SILU_TANH=0 / asyrp_set_silu_tanh(0): the 2-MUFU form.
+static int g_silu_tanh = -1;
+static int silu_tanh_enabled() {
+  if (g_silu_tanh < 0) {
+    const char* e = getenv("ASYRP_SILU_TANH");
+    g_silu_tanh = (e != nullptr) ? (e[0] != '0') : 1;
+  }
+  return g_silu_tanh;
 }
 // Does a conv with this tile configuration run as CTA pairs?  Two horizontally adjacent pixel tiles share each weight
 // tile: needs an even number of pixel tiles per sample (so that the pairing does not depend on the batch) and, at the
@@ -1410,7 +1488,7 @@ ASYRP_API int asyrp_conv_create(const AsyrpConvDesc* d, void** out_op) {
     p.seg[s].C = sg.C;
     p.seg[s].affine = sg.affine;
     p.seg[s].aff_stride = sg.affine_stride;
-    p.seg[s].act = sg.act;
+    p.seg[s].act = (sg.act == 1 && silu_tanh_enabled()) ? 2 : sg.act;
     ASYRP_REQUIRE(!(sg.affine != nullptr && sg.mode == 2), "asyrp_conv_create: no fused affine on stride-2 segments");
     if (sg.gn_gamma != nullptr) {
       ASYRP_REQUIRE(sg.affine == nullptr && sg.gn_sums_a != nullptr && sg.gn_beta != nullptr && sg.gn_Ca > 0 &&
@@ -1624,10 +1702,24 @@ ASYRP_API int asyrp_set_cta2(int enabled) {
   g_cta2 = enabled ? 1 : 0;
   return ASYRP_OK;
 }
+#ifdef ASYRP_TRACE
+// diagnostic build only: device buffer [grid][kTraceRoles][kTraceLen] int64 receiving the pipeline timeline
+ASYRP_API int asyrp_conv_set_trace(void* handle, long long* buf) {
+  ASYRP_REQUIRE(handle, "asyrp_conv_set_trace: null op");
+  static_cast<ConvOp*>(handle)->p.trace = buf;
+  return static_cast<ConvOp*>(handle)->grid;
+}
+#endif
 // CTA pairs for the 256 px x 128 ch tile (instead of the swapped-operand tile); affects ops created afterwards AND the
 // statistics-slot counts asyrp_conv_stats_tiles*() report — set it before building a plan
 ASYRP_API int asyrp_set_pair128(int enabled) {
   g_pair128 = enabled < 0 ? -1 : (enabled ? 1 : 0);  // negative: back to the default (ASYRP_PAIR128, else built-in)
+  return ASYRP_OK;
+}
+// SiLU of the fused operand transform: 1 = one tanh.approx (default), 0 = ex2 + rcp; negative: back to the default
+// (ASYRP_SILU_TANH).  Affects ops created afterwards.
+ASYRP_API int asyrp_set_silu_tanh(int enabled) {
+  g_silu_tanh = enabled < 0 ? -1 : (enabled ? 1 : 0);
   return ASYRP_OK;
 }
 // 1 if `op` runs as CTA pairs

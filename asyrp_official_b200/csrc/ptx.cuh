@@ -312,4 +312,13 @@ __device__ __forceinline__ float silu_fast(float x) {
   return x * r;
 }
 
+// SiLU from ONE special-function op: with h = x/2, x*sigmoid(x) = h + h*tanh(h).  tanh.approx.f32 carries 11 bits
+// (max relative error 2^-11): the absolute error is <= 2^-12 |x|, the size of the fp16 rounding the operand gets
+// anyway.  Takes h, not x: callers fold the 1/2 into the affine that precedes the activation.
+__device__ __forceinline__ float silu_tanh_half(float h) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
+
 }  // namespace asyrp

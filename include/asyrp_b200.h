@@ -149,6 +149,10 @@ int asyrp_set_cta2(int enabled);
  * a plan (ASYRP_PAIR128=0/1) */
 int asyrp_set_pair128(int enabled);
 int asyrp_conv_is_cta2(void* op);
+/* SiLU inside the fused GroupNorm-apply + SiLU operand transform: 1 (default) = h + h * tanh.approx(h), h = x / 2 (one
+ * special-function op, 11-bit tanh), 0 = x * rcp.approx(1 + ex2.approx(-x log2 e)); negative = default (ASYRP_SILU_TANH).
+ * Affects ops created afterwards. */
+int asyrp_set_silu_tanh(int enabled);
 int asyrp_conv_create(const AsyrpConvDesc* desc, void** op); /* encodes TMA descriptors; host only */
 int asyrp_conv_launch(void* op, void* stream);
 int asyrp_conv_set_scales(void* op, float acc_scale, float res_scale); /* hs_coeff of forward(), diffusion.py:512-516 */

@@ -588,6 +588,35 @@ def test_pair128_kernel_matches_reference_and_swapped_kernel(cuda_device, case):
     assert d <= 2.0 ** -9 * ref.abs().max().item(), f"pair128 vs swapped kernel: {d}"
 
 
+def test_fused_silu_one_mufu_vs_two_mufu(cuda_device):
+    """SiLU inside the operand transform: h + h*tanh.approx(h) (default, one special-function op) against
+    x*rcp(1 + ex2(-x log2 e)) and against the fp64 formula.  Stated bound: the element-wise error of the tanh form is
+    <= 2^-12 |x| + fp16 rounding, so the conv output (K = 1152 products) stays within 1.5e-3 of max|ref| either way."""
+    ops = _ops()
+    lib = ops._lib.load()
+    g = torch.Generator().manual_seed(43)
+    N, C, H = 2, 128, 64
+    x, w = _rand((N, C, H, H), g, 2.0), _rand((C, C, 3, 3), g, 1.0 / math.sqrt(9 * C))
+    aff = torch.stack([_rand((N, C), g) * 0.5 + 1.0, _rand((N, C), g) * 0.5], dim=-1).contiguous()
+    y = _h(x) * aff[..., 0].double()[:, :, None, None] + aff[..., 1].double()[:, :, None, None]
+    ref = F.conv2d(y * torch.sigmoid(y), _h(w), padding=1)   # operand NOT rounded: the bound covers its fp16 rounding
+    errs = []
+    try:
+        for mode in (1, 0):
+            lib.asyrp_set_silu_tanh(mode)
+            out = torch.zeros(N, H, H, C, dtype=torch.float16, device=cuda_device)
+            op = ops.ConvOp([(_nhwc_half(x, cuda_device), ops.MODE_3x3, aff.to(cuda_device), 0, 1)],
+                            ops.pack_conv_weight(w).to(cuda_device), out=out, stats=ops.new_stats(N, H, H, C, cuda_device, True))
+            op.launch()
+            torch.cuda.synchronize()
+            errs.append((_from_nhwc(out).double() - ref).abs().max().item() / ref.abs().max().item())
+    finally:
+        lib.asyrp_set_silu_tanh(-1)
+    print(f"fused SiLU conv, max-abs error / max|ref|: tanh form {errs[0]:.2e}, ex2+rcp form {errs[1]:.2e}")
+    assert errs[0] <= 1.5e-3 and errs[1] <= 1.5e-3, errs
+    assert errs[0] <= 2.0 * errs[1] + 2e-4, errs
+
+
 @pytest.mark.parametrize("Co,fused", [(3, False), (6, True)])
 def test_conv_out_narrow_tile(cuda_device, Co, fused):
     """conv_out as a 16-wide N tile (BN=16): 3 / 6 real channels, fp32 planar store, bias, optional fused GN+SiLU"""
