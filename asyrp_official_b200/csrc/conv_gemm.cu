@@ -1605,10 +1605,26 @@ ASYRP_API int asyrp_conv_create(const AsyrpConvDesc* d, void** out_op) {
     const uint32_t need = 2 * p.a_stage_bytes + 2 * p.l_stage_bytes;
     if (need + 3 * b_stage <= ring_budget) { p.a_stages = 2; p.l_stages = 2; }
   }
+#ifdef ASYRP_TRACE
+  if (const char* e = getenv("ASYRP_A_STAGES")) {  // diagnostic build: ring depths from the environment
+    const int v = atoi(e);
+    if (v >= 2 && !(op->BN == 128 && op->MT == 2)) p.a_stages = v;
+  }
+  if (const char* e = getenv("ASYRP_L_STAGES")) {
+    const int v = atoi(e);
+    if (v >= 2 && p.l_stages != 0) p.l_stages = v;
+  }
+#endif
   const uint32_t a_ring = p.a_stages * p.a_stage_bytes + p.l_stages * p.l_stage_bytes;
   while (p.l_stages == 0 && p.a_stages > 2 && p.a_stages * p.a_stage_bytes + 2 * b_stage > ring_budget) --p.a_stages;
   int bs = static_cast<int>((ring_budget - (p.l_stages ? a_ring : p.a_stages * p.a_stage_bytes)) / b_stage);
   p.b_stages = bs > 16 ? 16 : (bs < 2 ? 2 : bs);
+#ifdef ASYRP_TRACE
+  if (const char* e = getenv("ASYRP_B_STAGES_MAX")) {  // diagnostic build: cap the weight ring depth
+    const int cap = atoi(e);
+    if (cap >= 2 && p.b_stages > cap) p.b_stages = cap;
+  }
+#endif
   p.ebias = d->ebias;
   p.ebias_stride = d->ebias_stride;
   p.out_planar = d->out_planar;
