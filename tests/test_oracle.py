@@ -115,3 +115,32 @@ def test_mini_inversion_matches_reference(family):
         x = o_smp.denoising_step(x, torch.ones(2) * i, torch.ones(2) * j, model=fwd, logvars=logv, b=betas, eta=0.0,
                                  learn_sigma=learn_sigma)[0]
     _close(x, gold["inv_xT"], f"{family} inversion")
+
+
+def test_image_range_fixture_first_steps_match_reference():
+    """tests/golden/ddpm_celeba_bounded_t400.npz (the pipeline in the image range, full size; make_golden.py
+    bounded_fixture): the oracle's first inversion step from the stored image stays bounded and its first edit step from
+    the reference's x_T reproduces the reference's recorded max|x0_t| of that step."""
+    gold = np.load(os.path.join(G, "ddpm_celeba_bounded_t400.npz"))
+    cfg = o_ddpm.CELEBA_CFG
+    sd = synth.synth_state_dict(o_ddpm.ddpm_param_shapes(cfg, 1), 1234, "torch_default")
+    blk = torch.load(os.path.join(G, "checkpoint", "smiling_LC_CelebA_HQ_t999_ninv40_ngen40_0.pth"), map_location="cpu",
+                     weights_only=True)["0"]
+    for k, v in blk.items():
+        sd["layer_0." + k] = v
+    sd["conv_out.weight"] = sd["conv_out.weight"] * float(gold["gamma"])
+    sd["conv_out.bias"] = sd["conv_out.bias"] * float(gold["gamma"])
+    fwd = lambda *a, **k: o_ddpm.ddpm_forward(sd, cfg, *a, **k)  # noqa: E731
+    seq = gold["seq"].tolist()
+    betas = o_smp.make_betas()
+    assert float(np.abs(gold["x0_out"]).max()) < 2 and float(np.abs(gold["x_T"]).max()) < 2 and gold["x0t_absmax"].max() < 2
+    x_T = torch.from_numpy(gold["x_T"])
+    # first reverse step (t = t_0, an edit step: t >= t_edit), deterministic (t >= t_addnoise)
+    _, x0_t, _, _ = o_smp.denoising_step(x_T, torch.ones(1) * seq[-1], torch.ones(1) * seq[-2], model=fwd, b=betas, eta=0.0,
+                                         index=0, t_edit=int(gold["t_edit"]), hs_coeff=(1.0, 1.0))
+    ref = float(gold["x0t_absmax"][0])
+    assert abs(x0_t.abs().max().item() - ref) <= TOL * max(1.0, ref), (x0_t.abs().max().item(), ref)
+    # first inversion step of the stored image (t = 0 -> seq[1]): x_1 = sqrt(a_1) x0 + O(gamma)
+    x0 = torch.from_numpy(gold["x0_in"]).float()
+    x1 = o_smp.denoising_step(x0, torch.ones(1) * seq[0], torch.ones(1) * seq[1], model=fwd, b=betas, eta=0.0)[0]
+    assert (x1 - x0).abs().max().item() < 0.1 and x1.abs().max().item() < 1.1
