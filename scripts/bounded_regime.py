@@ -17,7 +17,6 @@ import sys
 import time
 
 import torch
-import torch.nn.functional as F
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from oracle import ddpm as od, emulate as em, sampler as osmp, synth  # noqa: E402
